@@ -1,0 +1,70 @@
+"""Generates tests/golden/ref_*.npz by running the UNMODIFIED reference
+(/root/reference/splib/spcpl.py, sputils.py, spdummy.py) under oracle/stubs.
+
+Run in the build container only (`python -m oracle.make_golden`); the fixtures are committed,
+so neither the CPU tests nor the GPU box need /root/reference.
+"""
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_driver  # noqa: E402
+from sp_coupler_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CASES = [  # name, ncol, nlev, nk, seed, dt, f_les, f_gcm, conservative
+    ("ref_L19", 2, 19, 160, 42, 900.0, 1.0, 1.0, False),      # config C1 shape (T21 test case)
+    ("ref_L91", 4, 91, 160, 43, 900.0, 1.0, 1.0, False),
+    ("ref_L137", 3, 137, 160, 46, 900.0, 0.5, 0.75, False),   # non-unit forcing factors
+    ("ref_L19_nk20", 3, 19, 20, 47, 600.0, 1.0, 1.0, False),  # spdummy-sized LES (8x8x20, dz=200)
+    ("ref_L91_cons", 3, 91, 160, 48, 900.0, 1.0, 1.0, True),  # --conservative_coarsening
+]
+
+
+def case_inputs(ncol, nlev, nk, seed):
+    dz = 25.0 if nk == 160 else 200.0
+    zf, zh = synth.les_grid(nk, dz)
+    gcm = synth.make_gcm_columns(ncol, nlev, seed=seed)
+    aux = synth.make_les_aux(ncol, nk, seed=seed)
+    plan = synth.les_volume_plan(gcm, zf)
+    rng = np.random.default_rng(seed + 7)
+    lp = {f: plan[f][0] + plan[f][1] * 0.01 * rng.normal(size=plan[f][0].shape) for f in ("THL", "QT", "U", "V")}
+    lp["QL"] = np.maximum(1e-5 * rng.normal(size=(ncol, nk)) + 5e-6, 0.0)
+    A = rng.integers(0, 65, (ncol, nlev)) / 64.0
+    return zf, zh, gcm, aux, lp, A
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    for name, ncol, nlev, nk, seed, dt, fl, fg, cons in CASES:
+        zf, zh, gcm, aux, lp, A = case_inputs(ncol, nlev, nk, seed)
+        out = ref_driver.run_columns(gcm, zf, zh, lp, aux, A, dt, fl, fg, True, conservative=cons)
+        blob = {"zf": zf, "zh": zh, "dt": dt, "f_les": fl, "f_gcm": fg, "conservative": cons, "A_les": A}
+        blob.update({"gcm_" + k: v for k, v in gcm.items()})
+        blob.update({"aux_" + k: v for k, v in aux.items()})
+        blob.update({"les_" + k: v for k, v in lp.items()})
+        blob.update({"out_" + k: v for k, v in out.items()})
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **blob)
+        print(name, "->", len(blob), "arrays")
+
+    # known-answer vectors of the reference's own tests, evaluated by the reference itself
+    sputils, spcpl, spdummy, spio = ref_driver.load_reference()
+    les = spdummy.dummy_les(1)
+    les.commit_grid()
+    les.zh_cache = les.get_zh()                       # as splib.initialize does (splib.py:152)
+    les.gcm_Zh = np.array([100000., 1000., 100., 10., 1., 0.])   # splib/test/spcpl_test.py:13
+    A = np.asarray(spcpl.get_cloud_fraction(les))
+    idx = sputils.searchsorted(les.zh_cache, les.gcm_Zh, side="right")[:-1:][::-1]
+    p = np.array([2e5, 2.03947e5, 12.03947e5, 1e5, 5e4, 101325.0])
+    np.savez(os.path.join(GOLDEN, "ref_kat.npz"),
+             cf_zh=np.asarray(les.zh_cache), cf_Zh=np.asarray(les.gcm_Zh), cf_idx=np.asarray(idx),
+             cf_A=A, cf_Aprofile=np.asarray(les.get_profile_field("A")),
+             p=p, exner=np.asarray(sputils.exner(p)), iexner=np.asarray(sputils.iexner(p)))
+    print("ref_kat -> idx", idx, "A", A)
+
+
+if __name__ == "__main__":
+    main()

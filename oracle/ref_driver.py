@@ -1,0 +1,113 @@
+"""Runs the UNMODIFIED reference coupler (/root/reference/splib/{spcpl,sputils}.py) per column
+under the unit shim in oracle/stubs — TEST INFRASTRUCTURE ONLY.
+
+Works only where /root/reference exists (the build container); it is used to
+(1) validate oracle/numpy_batched.py and (2) generate the golden vectors committed under
+tests/golden/ (oracle/make_golden.py). Nothing on the GPU box imports this module.
+"""
+import contextlib
+import io
+import os
+import sys
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("SPC_REFERENCE_ROOT", "/root/reference")
+_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
+
+
+def available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "splib", "spcpl.py"))
+
+
+def load_reference():
+    """Import splib.{sputils,spcpl,spdummy,spio} from the reference tree, unmodified."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    for p in (REFERENCE_ROOT, _STUBS):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from splib import sputils, spcpl, spdummy, spio  # noqa
+    return sputils, spcpl, spdummy, spio
+
+
+class _Les(object):
+    """Bare LES object with what spcpl reads/calls on the path."""
+
+    def __init__(self, idx):
+        self.grid_index = idx
+        self.sent = {}
+
+    def _setter(name):
+        def f(self, v, return_request=False):
+            self.sent[name] = np.array(v, dtype=np.float64)
+            return None
+        return f
+
+    set_tendency_U = _setter("f_u")
+    set_tendency_V = _setter("f_v")
+    set_tendency_THL = _setter("f_thl")
+    set_tendency_QT = _setter("f_qt")
+    set_tendency_surface_pressure = _setter("f_ps")
+    set_tendency_QL = _setter("f_ql")
+    set_ref_profile_QL = _setter("ql_ref")
+    set_z0m_surf = _setter("z0m")
+    set_z0h_surf = _setter("z0h")
+    set_wt_surf = _setter("wthl")
+    set_wq_surf = _setter("wqt")
+
+
+class _Gcm(object):
+    def __init__(self):
+        self.tend = {}
+
+    def set_profile_tendency(self, name, idx, vals):
+        self.tend.setdefault(idx, {})[name] = np.array(vals, dtype=np.float64)
+
+
+def run_columns(gcm, zf, zh, les_prof, aux, A_les, dt, f_les, f_gcm, couple_surface=True,
+                conservative=False):
+    """Drive reference set_les_forcings + set_gcm_tendencies for every column.
+
+    gcm: dict of [ncol, ...] float arrays (gcm_vars + surf_vars); les_prof: dict U,V,THL,QT,QL
+    [ncol, nk]; aux: dict presf,Rhof,Rhobf,QL_ice,QR,T [ncol,nk], PS, Rain [ncol]; A_les: [ncol,
+    nlev] cloud fraction in ascending slab order (profile["A"]). Returns dict of stacked outputs,
+    including every diagnostic the reference hands to spio.write_les_data."""
+    sputils, spcpl, spdummy, spio = load_reference()
+    from _q import Q
+    ncol = gcm["T"].shape[0]
+    captured = {}
+    spio.write_les_data = lambda les, **kw: captured.update(kw)
+    rows = []
+    for c in range(ncol):
+        captured.clear()
+        les = _Les(c)
+        for v in spcpl.gcm_vars:
+            setattr(les, v, Q(np.asarray(gcm[v][c], dtype=np.float64)))
+        for v in spcpl.surf_vars:
+            setattr(les, v, Q(np.float64(gcm[v][c])))
+        les.zf_cache = Q(np.asarray(zf, dtype=np.float64))
+        les.zh_cache = Q(np.asarray(zh, dtype=np.float64))
+        les.rain = Q(0.0)
+        prof = {k: Q(np.asarray(les_prof[k][c], dtype=np.float64)) for k in ("U", "V", "THL", "QT", "QL")}
+        for k in ("presf", "Rhof", "Rhobf", "QL_ice", "QR", "T"):
+            prof[k] = Q(np.asarray(aux[k][c], dtype=np.float64))
+        prof["PS"] = Q(np.float64(aux["PS"][c]))
+        prof["Rain"] = Q(np.float64(aux["Rain"][c]))
+        prof["A"] = Q(np.asarray(A_les[c], dtype=np.float64))
+        g = _Gcm()
+        spcpl.set_les_forcings(les, None, False, False, prof, dt, f_les, couple_surface, write=True)
+        # cloud-fraction slab mapping exactly as get_les_profiles builds it (spcpl.py:761-764)
+        idx = sputils.searchsorted(les.zh_cache, les.gcm_Zh, side="right")[:-1:][::-1]
+        # sputils.integral prints a length warning per call when len(zh) == len(q) (sputils.py:111)
+        with contextlib.redirect_stdout(io.StringIO()):
+            spcpl.set_gcm_tendencies(g, les, prof, dt, f_gcm, write=True, conservative=conservative)
+        row = {k: np.array(v, dtype=np.float64) for k, v in captured.items()}
+        row.update({k: v for k, v in les.sent.items()})
+        row.update({"f_" + k: v for k, v in g.tend[c].items()})
+        row["slab_idx"] = np.asarray(idx, dtype=np.int32)
+        row["gcm_Zf"] = np.array(les.gcm_Zf, dtype=np.float64)
+        row["gcm_Zh"] = np.array(les.gcm_Zh, dtype=np.float64)
+        row["start_index"] = np.int32(sputils.searchsorted(-les.gcm_Zf, -les.zf_cache[-1]))  # spcpl.py:498
+        rows.append(row)
+    keys = rows[0].keys()
+    return {k: np.stack([r[k] for r in rows]) for k in keys}
