@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI in include/spcpl_b200.h (libspcpl_b200.so, built by build.py).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libspcpl_b200.so")
+
+SPC_F32, SPC_F64 = 0, 1
+LAYOUT_KJI, LAYOUT_IJK = 0, 1
+NFIELDS, NTEND = 5, 7
+
+# every symbol include/spcpl_b200.h declares (checked by tests/test_abi.py against the header)
+SYMBOLS = ["spc_abi_version", "spc_last_error", "spc_create", "spc_destroy", "spc_mask_words_per_column",
+           "spc_slab_reduce", "spc_gcm_to_les", "spc_les_to_gcm", "spc_interp", "spc_searchsorted", "spc_exner",
+           "spc_set_les_state"]
+
+_vp, _i, _d = C.c_void_p, C.c_int, C.c_double
+
+
+class GcmCols(C.Structure):
+    """struct spc_gcm_cols"""
+    _fields_ = [("ncol", _i), ("nlev", _i), ("dtype", _i)] + [(n, _vp) for n in (
+        "U", "V", "T", "SH", "QL", "QI", "Pfull", "A", "Zgfull", "Phalf", "Zghalf",
+        "Z0M", "Z0H", "QLflux", "QIflux", "SHflux", "TLflux", "TSflux")]
+
+
+class LesForcing(C.Structure):
+    """struct spc_les_forcing"""
+    _fields_ = [(n, _vp) for n in (
+        "f_u", "f_v", "f_thl", "f_qt", "f_ql", "ql_ref", "u", "v", "thl", "qt", "f_ps", "ps",
+        "z0m", "z0h", "wthl", "wqt", "Tv", "THL", "QT", "Zf", "Zh", "bracket", "slab_idx")]
+
+
+class LesProf(C.Structure):
+    """struct spc_les_prof"""
+    _fields_ = [(n, _vp) for n in ("prof", "QL_ice", "T", "Rhobf", "A", "mask", "slab_idx")] + \
+               [(n, _i) for n in ("vol_dtype", "layout", "nx", "ny")]
+
+
+class GcmTend(C.Structure):
+    """struct spc_gcm_tend"""
+    _fields_ = [(n, _vp) for n in ("tend", "t", "A_d", "cntslab", "bracket", "bracket_pf", "start_index")]
+
+
+_lib = None
+
+
+def lib():
+    """Load libspcpl_b200.so once; raise loudly if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "sp_coupler_b200: CUDA library %s is missing. Build it with `python -m sp_coupler_b200.build` "
+            "(there is no CPU fallback)." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.spc_abi_version.restype = _i
+    L.spc_last_error.restype = C.c_char_p
+    L.spc_create.argtypes = [C.POINTER(_vp), _i]
+    L.spc_destroy.argtypes = [_vp]
+    L.spc_mask_words_per_column.restype = C.c_size_t
+    L.spc_mask_words_per_column.argtypes = [_i, _i, _i, _i, _i]
+    L.spc_slab_reduce.argtypes = [_vp, C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp]
+    L.spc_gcm_to_les.argtypes = [_vp, C.POINTER(GcmCols), _vp, _vp, _i, _vp, _vp, _d, _d, _i,
+                                 C.POINTER(LesForcing), _vp]
+    L.spc_les_to_gcm.argtypes = [_vp, C.POINTER(GcmCols), _vp, _vp, _i, C.POINTER(LesProf), _d, _d, _i,
+                                 C.POINTER(GcmTend), _vp]
+    L.spc_interp.argtypes = [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]
+    L.spc_searchsorted.argtypes = [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]
+    L.spc_exner.argtypes = [_vp, _i, _vp, C.c_size_t, _i, _vp, _vp]
+    L.spc_set_les_state.argtypes = [_vp, _vp, _d, C.c_uint32, C.c_uint32, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]
+    for name in SYMBOLS:
+        f = getattr(L, name)
+        if f.restype is C.c_int and name not in ("spc_abi_version",):
+            f.restype = _i
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().spc_last_error()
+        raise RuntimeError("%s failed (status %d): %s" % (what, rc, msg.decode() if msg else ""))

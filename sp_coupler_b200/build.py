@@ -1,0 +1,71 @@
+"""In-tree build of the CUDA C-ABI library (sm_100a only) with plain nvcc.
+
+    python -m sp_coupler_b200.build [--force] [--verbose]
+
+Produces sp_coupler_b200/lib/libspcpl_b200.so (git-ignored; it travels to the GPU box with the
+gpurun snapshot). nvcc cross-compiles without a GPU. No torch headers are needed: the boundary is
+a C ABI (include/spcpl_b200.h) that the host side binds with ctypes.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+LIB = os.path.join(LIBDIR, "libspcpl_b200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+# translation unit -> extra flags. The profile kernels are compiled without FMA contraction so
+# that float64 results are bit-identical to numpy's ("Numerics").
+SOURCES = {
+    "spc_abi.cu": [],
+    "slab_reduce.cu": [],
+    "profiles.cu": ["--fmad=false"],
+    "les_state.cu": ["--fmad=false"],
+}
+
+
+def nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; the CUDA extension cannot be built")
+    return exe
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    headers = [os.path.join(ROOT, "include", "spcpl_b200.h"), os.path.join(CSRC, "spc_common.cuh"), __file__]
+    objs, rebuilt = [], False
+    for src, extra in SOURCES.items():
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            cmd = [nvcc()] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.check_call(cmd)
+            rebuilt = True
+    if rebuilt or not os.path.exists(LIB):
+        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

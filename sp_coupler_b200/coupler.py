@@ -1,0 +1,298 @@
+"""Batched host interface of the coupling kernels over torch device tensors.
+
+`Coupler` owns one C-ABI handle per device and exposes the path's operations over `[ncol, ...]`
+tensors. torch is plumbing only (device memory, streams); every number is produced by the
+hand-written sm_100a kernels behind include/spcpl_b200.h. There is no CPU path: CPU tensors are
+rejected, and a missing library raises at first use.
+"""
+import ctypes as C
+
+import torch
+
+from . import _abi
+from .constants import LES_FIELDS, TENDENCIES, gcm_vars, surf_vars
+
+_DT = {torch.float32: _abi.SPC_F32, torch.float64: _abi.SPC_F64}
+_LAYOUT = {"kji": _abi.LAYOUT_KJI, "ijk": _abi.LAYOUT_IJK, 0: 0, 1: 1}
+GCM_FULL = ("U", "V", "T", "SH", "QL", "QI", "Pfull", "A", "Zgfull")
+GCM_HALF = ("Phalf", "Zghalf")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Coupler(object):
+    """Per-device entry point. All methods are asynchronous on torch's current stream."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sp_coupler_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._lib = _abi.lib()
+        h = C.c_void_p()
+        _abi.check(self._lib.spc_create(C.byref(h), self.device.index), "spc_create")
+        self._h = h
+        self.launches = 0   # kernels launched through this handle (bench.py's gpu_launches)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.spc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, t, name, dtype=None, shape=None):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError("%s must be a torch tensor" % name)
+        if t.device != self.device:
+            raise ValueError("%s is on %s, expected %s" % (name, t.device, self.device))
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % name)
+        if dtype is not None and t.dtype != dtype:
+            raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+        return t
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def _gcm_struct(self, gcm, couple_surface):
+        T = gcm["T"]
+        dtype = T.dtype
+        if dtype not in _DT:
+            raise TypeError("GCM profiles must be float32 or float64")
+        ncol, nlev = T.shape
+        s = _abi.GcmCols()
+        s.ncol, s.nlev, s.dtype = ncol, nlev, _DT[dtype]
+        for n in GCM_FULL:
+            setattr(s, n, self._chk(gcm[n], n, dtype, (ncol, nlev)).data_ptr())
+        for n in GCM_HALF:
+            setattr(s, n, self._chk(gcm[n], n, dtype, (ncol, nlev + 1)).data_ptr())
+        if couple_surface:
+            for n in surf_vars:
+                if n == "TLflux" and n not in gcm:
+                    continue
+                setattr(s, n, self._chk(gcm[n], n, dtype, (ncol,)).data_ptr())
+        return s, ncol, nlev, dtype
+
+    # ------------------------------------------------------------------ K1
+    def mask_words_per_column(self, dtype, layout, nx, ny, nk):
+        return int(self._lib.spc_mask_words_per_column(_DT[dtype], _LAYOUT[layout], nx, ny, nk))
+
+    def slab_reduce(self, vols, layout="kji", ql_thresh=0.0, want_cnt=True, want_mask=True, out=None):
+        """Slab means + cloud count of the five LES volumes (spcpl.py:747-759,765).
+
+        vols: dict or sequence (THL,QT,QL,U,V) of [ncol,nk,ny,nx] ('kji') or [ncol,nx,ny,nk] ('ijk').
+        Returns dict(prof=[5,ncol,nk] f64, cnt=[ncol,nk] i32 | None, mask | None, nx, ny, dtype, layout)."""
+        v = [vols[f] for f in LES_FIELDS] if isinstance(vols, dict) else list(vols)
+        lay = _LAYOUT[layout]
+        dtype = v[0].dtype
+        if lay == _abi.LAYOUT_KJI:
+            ncol, nk, ny, nx = v[0].shape
+        else:
+            ncol, nx, ny, nk = v[0].shape
+        for i, t in enumerate(v):
+            self._chk(t, "vol[%s]" % LES_FIELDS[i], dtype, v[0].shape)
+        out = {} if out is None else out
+        prof = out.get("prof")
+        if prof is None:
+            prof = self._empty((5, ncol, nk), torch.float64)
+        cnt = out.get("cnt") if want_cnt else None
+        if want_cnt and cnt is None:
+            cnt = self._empty((ncol, nk), torch.int32)
+        mask = None
+        if want_mask:
+            mw = self.mask_words_per_column(dtype, lay, nx, ny, nk)
+            if mw == 0:
+                raise RuntimeError("no cloud-mask format for layout %r; pass want_mask=False" % (layout,))
+            mask = out.get("mask")
+            if mask is None:
+                mask = self._empty((ncol, mw), torch.int32)
+        arr = (C.c_void_p * 5)(*[t.data_ptr() for t in v])
+        _abi.check(self._lib.spc_slab_reduce(self._h, arr, _DT[dtype], lay, ncol, nx, ny, nk, float(ql_thresh),
+                                             _ptr(prof), _ptr(cnt), _ptr(mask), self._stream()), "spc_slab_reduce")
+        self.launches += 1
+        return dict(prof=prof, cnt=cnt, mask=mask, nx=nx, ny=ny, dtype=dtype, layout=lay)
+
+    # ------------------------------------------------------------------ K2
+    def gcm_to_les(self, gcm, zf, zh=None, les_prof=None, ps_les=None, dt=900.0, factor=1.0,
+                   couple_surface=True, diagnostics=False, want_state=False, want_bracket=False):
+        """convert_profiles + set_les_forcings arithmetic + convert_surface_fluxes for all columns
+        (spcpl.py:171-246, 299-385, 136-167). Returns a dict of output tensors."""
+        s, ncol, nlev, dtype = self._gcm_struct(gcm, couple_surface)
+        nk = zf.shape[0]
+        self._chk(zf, "zf", torch.float64, (nk,))
+        if zh is not None:
+            self._chk(zh, "zh", torch.float64, (nk,))
+        if les_prof is not None:
+            self._chk(les_prof, "les_prof", torch.float64, (5, ncol, nk))
+        if ps_les is not None:
+            self._chk(ps_les, "ps_les", dtype, (ncol,))
+        o = _abi.LesForcing()
+        res = {}
+
+        def alloc(name, shape, dt_=dtype):
+            t = self._empty(shape, dt_)
+            res[name] = t
+            setattr(o, name, t.data_ptr())
+
+        alloc("ql_ref", (ncol, nk))
+        alloc("ps", (ncol,))
+        if les_prof is not None:
+            for n in ("f_u", "f_v", "f_thl", "f_qt", "f_ql"):
+                alloc(n, (ncol, nk))
+        if ps_les is not None:
+            alloc("f_ps", (ncol,))
+        if want_state:
+            for n in ("u", "v", "thl", "qt"):
+                alloc(n, (ncol, nk))
+        if couple_surface:
+            for n in ("z0m", "z0h", "wthl", "wqt"):
+                alloc(n, (ncol,))
+        if diagnostics:
+            for n in ("Tv", "THL", "QT", "Zf"):
+                alloc(n, (ncol, nlev))
+            alloc("Zh", (ncol, nlev + 1))
+        if want_bracket:
+            alloc("bracket", (ncol, nk), torch.int32)
+        if zh is not None:
+            alloc("slab_idx", (ncol, nlev), torch.int32)
+        _abi.check(self._lib.spc_gcm_to_les(self._h, C.byref(s), _ptr(zf), _ptr(zh), nk, _ptr(les_prof), _ptr(ps_les),
+                                            float(dt), float(factor), int(bool(couple_surface)), C.byref(o),
+                                            self._stream()), "spc_gcm_to_les")
+        self.launches += 1
+        return res
+
+    # ------------------------------------------------------------------ K3
+    def les_to_gcm(self, gcm, zf, zh, slab, aux, slab_idx=None, dt=900.0, factor=1.0, conservative=False,
+                   A=None, diagnostics=False, tend_out=None):
+        """set_gcm_tendencies for all columns (spcpl.py:388-555) incl. the projected cloud fraction.
+
+        slab: result of slab_reduce (or a dict with 'prof'); aux: dict QL_ice, T (+Rhobf) [ncol,nk].
+        Returns dict(tend=[ncol,7,nlev], named views f_T.., A_d, start_index, ...)."""
+        s, ncol, nlev, dtype = self._gcm_struct(gcm, False)
+        nk = zf.shape[0]
+        self._chk(zf, "zf", torch.float64, (nk,))
+        if zh is not None:
+            self._chk(zh, "zh", torch.float64, (nk,))
+        lp = _abi.LesProf()
+        lp.prof = self._chk(slab["prof"], "slab.prof", torch.float64, (5, ncol, nk)).data_ptr()
+        lp.QL_ice = self._chk(aux["QL_ice"], "QL_ice", dtype, (ncol, nk)).data_ptr()
+        lp.T = self._chk(aux["T"], "T", dtype, (ncol, nk)).data_ptr()
+        if conservative:
+            lp.Rhobf = self._chk(aux["Rhobf"], "Rhobf", dtype, (ncol, nk)).data_ptr()
+        if A is not None:
+            lp.A = self._chk(A, "A", dtype, (ncol, nlev)).data_ptr()
+        elif slab.get("mask") is not None:
+            if slab_idx is None:
+                raise ValueError("slab_idx (from gcm_to_les) is needed to project the cloud mask")
+            lp.mask = slab["mask"].data_ptr()
+            lp.slab_idx = self._chk(slab_idx, "slab_idx", torch.int32, (ncol, nlev)).data_ptr()
+            lp.vol_dtype, lp.layout, lp.nx, lp.ny = _DT[slab["dtype"]], slab["layout"], slab["nx"], slab["ny"]
+        o = _abi.GcmTend()
+        tend = tend_out if tend_out is not None else self._empty((ncol, 7, nlev), dtype)
+        self._chk(tend, "tend", dtype, (ncol, 7, nlev))
+        o.tend = tend.data_ptr()
+        res = {"tend": tend}
+
+        def alloc(name, shape, dt_=dtype):
+            t = self._empty(shape, dt_)
+            res[name] = t
+            setattr(o, name, t.data_ptr())
+
+        alloc("A_d", (ncol, nlev))
+        alloc("start_index", (ncol,), torch.int32)
+        if lp.mask:
+            alloc("cntslab", (ncol, nlev), torch.int32)
+        if diagnostics:
+            alloc("t", (ncol, nk))
+            alloc("bracket", (ncol, nlev), torch.int32)
+            alloc("bracket_pf", (ncol, nk), torch.int32)
+        _abi.check(self._lib.spc_les_to_gcm(self._h, C.byref(s), _ptr(zf), _ptr(zh), nk, C.byref(lp), float(dt),
+                                            float(factor), int(bool(conservative)), C.byref(o), self._stream()),
+                   "spc_les_to_gcm")
+        self.launches += 1
+        for i, n in enumerate(TENDENCIES):
+            res[n] = tend[:, i, :]
+        return res
+
+    # ------------------------------------------------------------------ sputils helpers
+    def interp(self, x, xp, fp, want_bracket=False):
+        """numpy.interp over a batch of rows (sputils.py:82-86). x: [nx] or [nb,nx]; xp, fp: [nb,np]."""
+        dtype = xp.dtype
+        nb, np_ = xp.shape
+        self._chk(xp, "xp", dtype)
+        self._chk(fp, "fp", dtype, (nb, np_))
+        batched = x.dim() == 2
+        nx = x.shape[-1]
+        self._chk(x, "x", dtype, (nb, nx) if batched else (nx,))
+        out = self._empty((nb, nx), dtype)
+        br = self._empty((nb, nx), torch.int32) if want_bracket else None
+        _abi.check(self._lib.spc_interp(self._h, _DT[dtype], _ptr(x), int(batched), _ptr(xp), _ptr(fp), nb, nx, np_,
+                                        _ptr(out), _ptr(br), self._stream()), "spc_interp")
+        self.launches += 1
+        return (out, br) if want_bracket else out
+
+    def searchsorted(self, a, v, side="left"):
+        """numpy.searchsorted over a batch of rows (sputils.py:88-91). a: [nb,na]; v: [nv] or [nb,nv]."""
+        dtype = a.dtype
+        nb, na = a.shape
+        self._chk(a, "a", dtype)
+        batched = v.dim() == 2
+        nv = v.shape[-1]
+        self._chk(v, "v", dtype, (nb, nv) if batched else (nv,))
+        out = self._empty((nb, nv), torch.int32)
+        _abi.check(self._lib.spc_searchsorted(self._h, _DT[dtype], _ptr(a), _ptr(v), int(batched), nb, na, nv,
+                                              int(side == "right"), _ptr(out), self._stream()), "spc_searchsorted")
+        self.launches += 1
+        return out
+
+    def exner(self, p, inverse=False):
+        """(p/pref0)^(+-rd/cp) (sputils.py:28-34)."""
+        self._chk(p, "p")
+        out = torch.empty_like(p)
+        _abi.check(self._lib.spc_exner(self._h, _DT[p.dtype], _ptr(p), p.numel(), int(inverse), _ptr(out),
+                                       self._stream()), "spc_exner")
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ set_les_state
+    def set_les_state(self, prof, amp, stream_id, nx, ny, seed=42, col0=0, sub=None, clamp0=False,
+                      dtype=torch.float32, out=None):
+        """Profile -> [ncol,nk,ny,nx] volume with uniform noise (spcpl.py:274-294), Philox4x32-10."""
+        ncol, nk = prof.shape
+        self._chk(prof, "prof", torch.float64)
+        if sub is not None:
+            self._chk(sub, "sub", torch.float64, (ncol, nk))
+        vol = out if out is not None else self._empty((ncol, nk, ny, nx), dtype)
+        self._chk(vol, "vol", dtype, (ncol, nk, ny, nx))
+        _abi.check(self._lib.spc_set_les_state(self._h, _ptr(prof), float(amp), int(stream_id), int(seed), int(col0),
+                                               _ptr(sub), int(bool(clamp0)), _ptr(vol), _DT[dtype], ncol, nx, ny, nk,
+                                               self._stream()), "spc_set_les_state")
+        self.launches += 1
+        return vol
+
+
+_default = {}
+
+
+def default_coupler(device=None):
+    """Process-wide Coupler per device."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    if dev not in _default:
+        _default[dev] = Coupler(dev)
+    return _default[dev]

@@ -1,0 +1,107 @@
+// spc_set_les_state: profile -> volume broadcast with uniform noise (spcpl.set_les_state,
+// splib/spcpl.py:274-294), HBM-write-bound. Noise comes from counter-based Philox4x32-10 so that
+// the volume is a pure function of (seed, stream, global column, element) — identical on any
+// sharding and reproducible on the host (sp_coupler_b200/synth.py: les_state_volume).
+// Compiled with --fmad=false: prof + amp*n - sub is evaluated exactly as numpy does.
+#include "spc_common.cuh"
+
+namespace {
+
+constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(kM0, c.x), lo0 = kM0 * c.x;
+    const uint32_t hi1 = __umulhi(kM1, c.z), lo1 = kM1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += kW0;
+    k1 += kW1;
+  }
+  return c;
+}
+
+__device__ __forceinline__ double noise(uint32_t x) {
+  const double u = (double)(x >> 8) * (1.0 / 16777216.0);
+  return 2.0 * u - 1.0;
+}
+
+struct K5Args {
+  const double *prof, *sub;
+  void* vol;
+  double amp;
+  uint32_t stream_id, seed;
+  int col0, clamp0, ncol, nk;
+  long long S, nE, ngrp;  // slab elements, elements per column, Philox groups per column
+};
+
+template <typename T>
+__device__ __forceinline__ double value(const K5Args& a, int c, long long e, uint32_t x) {
+  const int k = (int)(e / a.S);
+  double v = __ldg(a.prof + (size_t)c * a.nk + k) + a.amp * noise(x);
+  if (a.sub) v = v - __ldg(a.sub + (size_t)c * a.nk + k);
+  if (a.clamp0) v = fmax(v, 0.0);
+  return (double)(T)v;
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) les_state_kernel(const K5Args a) {
+  const long long total = a.ngrp * a.ncol;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t / a.ngrp);
+    const long long g = t - (long long)c * a.ngrp;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(a.col0 + c), a.stream_id), a.seed,
+                                  0x5BD1E995u);
+    const long long e0 = g * 4;
+    T* out = static_cast<T*>(a.vol) + (size_t)c * a.nE;
+    const uint32_t x[4] = {r.x, r.y, r.z, r.w};
+    if constexpr (VEC) {
+      T v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (T)value<T>(a, c, e0 + i, x[i]);
+      if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(out + e0) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        *reinterpret_cast<double2*>(out + e0) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(out + e0 + 2) = make_double2(v[2], v[3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (e0 + i < a.nE) out[e0 + i] = (T)value<T>(a, c, e0 + i, x[i]);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int spc_set_les_state(spc_handle h, const double* prof, double amp, uint32_t stream_id, uint32_t seed, int col0,
+                                 const double* sub, int clamp0, void* vol, int dtype, int ncol, int nx, int ny, int nk,
+                                 void* stream) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  SPC_REQUIRE(dtype == SPC_F32 || dtype == SPC_F64, SPC_ERR_ARG, "spc_set_les_state: bad dtype %d", dtype);
+  SPC_REQUIRE(ncol >= 0 && nx > 0 && ny > 0 && nk > 0, SPC_ERR_ARG, "spc_set_les_state: bad shape");
+  if (ncol == 0) return SPC_OK;
+  SPC_REQUIRE(prof && vol, SPC_ERR_ARG, "spc_set_les_state: NULL pointer");
+  spc::DeviceGuard guard(h->device);
+  K5Args a;
+  a.prof = prof; a.sub = sub; a.vol = vol; a.amp = amp; a.stream_id = stream_id; a.seed = seed;
+  a.col0 = col0; a.clamp0 = clamp0; a.ncol = ncol; a.nk = nk;
+  a.S = (long long)nx * ny;
+  a.nE = a.S * nk;
+  a.ngrp = (a.nE + 3) / 4;
+  const bool vec = (a.nE % 4 == 0) && (reinterpret_cast<uintptr_t>(vol) % 16 == 0);
+  const long long total = a.ngrp * ncol;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SPC_F32) {
+    if (vec) les_state_kernel<float, true><<<grid, 256, 0, st>>>(a);
+    else les_state_kernel<float, false><<<grid, 256, 0, st>>>(a);
+  } else {
+    if (vec) les_state_kernel<double, true><<<grid, 256, 0, st>>>(a);
+    else les_state_kernel<double, false><<<grid, 256, 0, st>>>(a);
+  }
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
+}

@@ -1,0 +1,491 @@
+// K2 gcm_to_les, K3 les_to_gcm and the sputils batch helpers (interp / searchsorted / exner).
+//
+// One thread block per superparameterized column; the column's GCM profiles are converted once
+// into shared memory (heights, theta_l, q_t, reversed to ascending height) and every LES / GCM
+// level is then handled by one thread: bracket search in shared memory + all interpolations +
+// the relaxation forcing, fused. All arithmetic is float64 and this file is compiled with
+// --fmad=false so that float64 results are bit-identical to numpy's wherever numpy's own
+// operations are correctly rounded (everything except pow, which CUDA evaluates to <= 2 ulp).
+#include "spc_common.cuh"
+
+namespace {
+
+using namespace spc;
+
+constexpr int kThreads = 256;
+constexpr double kC = rv / rd - 1;          // spcpl.py:175
+constexpr double kExp = rd / cp;            // sputils.py:29
+constexpr double kIExp = -rd / cp;          // sputils.py:34
+
+struct GcmPtrs {
+  const void *U, *V, *T, *SH, *QL, *QI, *Pfull, *A, *Zgfull, *Phalf, *Zghalf;
+  const void *Z0M, *Z0H, *QLflux, *QIflux, *SHflux, *TLflux, *TSflux;
+  int ncol, nlev;
+};
+
+GcmPtrs to_ptrs(const spc_gcm_cols* g) {
+  GcmPtrs p;
+  p.U = g->U; p.V = g->V; p.T = g->T; p.SH = g->SH; p.QL = g->QL; p.QI = g->QI; p.Pfull = g->Pfull; p.A = g->A;
+  p.Zgfull = g->Zgfull; p.Phalf = g->Phalf; p.Zghalf = g->Zghalf;
+  p.Z0M = g->Z0M; p.Z0H = g->Z0H; p.QLflux = g->QLflux; p.QIflux = g->QIflux; p.SHflux = g->SHflux;
+  p.TLflux = g->TLflux; p.TSflux = g->TSflux;
+  p.ncol = g->ncol; p.nlev = g->nlev;
+  return p;
+}
+
+template <typename T>
+__device__ __forceinline__ double ld(const void* p, size_t i) {
+  return (double)__ldg(static_cast<const T*>(p) + i);
+}
+template <typename T>
+__device__ __forceinline__ void st(void* p, size_t i, double v) {
+  if (p) static_cast<T*>(p)[i] = (T)v;
+}
+
+// ------------------------------------------------------------------------------------------ K2
+struct K2Args {
+  GcmPtrs g;
+  const double *zf, *zh, *les_prof;
+  const void* ps_les;
+  spc_les_forcing o;
+  double dt, factor;
+  int nk, couple_surface;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) gcm_to_les_kernel(const K2Args a) {
+  extern __shared__ __align__(16) double sm[];
+  const int nlev = a.g.nlev, nk = a.nk, ncol = a.g.ncol;
+  const int c = blockIdx.x;
+  double* Zf = sm;               // ascending (reversed GCM order), spcpl.py:224-228
+  double* thl = Zf + nlev;
+  double* qt = thl + nlev;
+  double* ql = qt + nlev;
+  double* u = ql + nlev;
+  double* v = u + nlev;
+  const size_t b = (size_t)c * nlev, bh = (size_t)c * (nlev + 1);
+  const double zs = ld<T>(a.g.Zghalf, bh + nlev);   // Zghalf[-1]
+  const spc_les_forcing& o = a.o;
+
+  for (int l = threadIdx.x; l <= nlev; l += kThreads) {
+    const double Zh = (ld<T>(a.g.Zghalf, bh + l) - zs) / grav;          // spcpl.py:197
+    st<T>(o.Zh, bh + l, Zh);
+    if (l < nlev && o.slab_idx && a.zh) {
+      // searchsorted(zh, Zh, side="right")[:-1][::-1]  (spcpl.py:26,764)
+      o.slab_idx[b + (nlev - 1 - l)] = upper_bound(a.zh, nk, Zh);
+    }
+    if (l == nlev) break;
+    const double Tl = ld<T>(a.g.T, b + l), SH = ld<T>(a.g.SH, b + l);
+    const double QL = ld<T>(a.g.QL, b + l), QI = ld<T>(a.g.QI, b + l);
+    const double Pf = ld<T>(a.g.Pfull, b + l);
+    const double Tv = Tl * (1 + kC * SH - (QL + QI));                    // spcpl.py:176
+    const double zf_l = (ld<T>(a.g.Zgfull, b + l) - zs) / grav;         // spcpl.py:198
+    const double thl_ = (Tl - (rlv * (QL + QI)) / cp) * pow(Pf / pref0, kIExp);  // spcpl.py:214
+    const double qt_ = SH + QL + QI;                                     // spcpl.py:215
+    const int r = nlev - 1 - l;
+    Zf[r] = zf_l;
+    thl[r] = thl_;
+    qt[r] = qt_;
+    ql[r] = QL;
+    u[r] = ld<T>(a.g.U, b + l);
+    v[r] = ld<T>(a.g.V, b + l);
+    st<T>(o.Tv, b + l, Tv);
+    st<T>(o.Zf, b + l, zf_l);
+    st<T>(o.THL, b + l, thl_);
+    st<T>(o.QT, b + l, qt_);
+  }
+  if (threadIdx.x == 0) {
+    const double ps = ld<T>(a.g.Phalf, bh + nlev);                       // Ph[-1], spcpl.py:246
+    st<T>(o.ps, c, ps);
+    if (o.f_ps) st<T>(o.f_ps, c, a.factor * (ps - ld<T>(a.ps_les, c)) / a.dt);   // spcpl.py:332
+    if (a.couple_surface) {                                              // spcpl.py:136-167
+      const double rho = ps / (rd * ld<T>(a.g.T, b + nlev - 1));
+      const double wqt = -(ld<T>(a.g.QLflux, c) + ld<T>(a.g.QIflux, c) + ld<T>(a.g.SHflux, c)) / rho;
+      const double wthl = -ld<T>(a.g.TSflux, c) * pow(ps / pref0, kIExp) / (cp * rho);
+      st<T>(o.z0m, c, ld<T>(a.g.Z0M, c));
+      st<T>(o.z0h, c, ld<T>(a.g.Z0H, c));
+      st<T>(o.wthl, c, wthl);
+      st<T>(o.wqt, c, wqt);
+    }
+  }
+  __syncthreads();
+
+  const size_t pf = (size_t)ncol * nk;   // field stride of les_prof [5][ncol][nk]
+  for (int k = threadIdx.x; k < nk; k += kThreads) {
+    const double x = __ldg(a.zf + k);
+    const int j = upper_bound(Zf, nlev, x) - 1;
+    const size_t i = (size_t)c * nk + k;
+    const double thl_g = interp_at(Zf, thl, nlev, x, j);
+    const double qt_g = interp_at(Zf, qt, nlev, x, j);
+    const double ql_g = interp_at(Zf, ql, nlev, x, j);
+    const double u_g = interp_at(Zf, u, nlev, x, j);
+    const double v_g = interp_at(Zf, v, nlev, x, j);
+    if (o.bracket) o.bracket[i] = j;
+    st<T>(o.thl, i, thl_g);
+    st<T>(o.qt, i, qt_g);
+    st<T>(o.u, i, u_g);
+    st<T>(o.v, i, v_g);
+    st<T>(o.ql_ref, i, ql_g);
+    if (a.les_prof) {                                                    // spcpl.py:328-333
+      st<T>(o.f_u, i, a.factor * (u_g - __ldg(a.les_prof + SPC_U * pf + i)) / a.dt);
+      st<T>(o.f_v, i, a.factor * (v_g - __ldg(a.les_prof + SPC_V * pf + i)) / a.dt);
+      st<T>(o.f_thl, i, a.factor * (thl_g - __ldg(a.les_prof + SPC_THL * pf + i)) / a.dt);
+      st<T>(o.f_qt, i, a.factor * (qt_g - __ldg(a.les_prof + SPC_QT * pf + i)) / a.dt);
+      st<T>(o.f_ql, i, a.factor * (ql_g - __ldg(a.les_prof + SPC_QL * pf + i)) / a.dt);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K3
+struct K3Args {
+  GcmPtrs g;
+  const double *zf, *zh;
+  spc_les_prof les;
+  spc_gcm_tend o;
+  double dt, factor;
+  int nk, conservative, mask_words;  // mask words per (column, level)
+};
+
+// sputils.integral, weighted branch (sputils.py:94-161), a <= b guaranteed by the caller
+// (a = Zh[i+1] < b = Zh[i]); z has n entries, q/w are cell values on [z[i], z[i+1]].
+__device__ double integral_w(double a, double b, const double* z, int n, const double* q, const double* w) {
+  int ia = 0;
+  while (ia + 1 < n - 1 && z[ia + 1] < a) ++ia;                         // sputils.py:123-124
+  int ib = ia;
+  while (ib + 1 < n - 1 && z[ib + 1] < b) ++ib;                         // sputils.py:126-127
+  double S = 0.0, Sw = 0.0;
+  for (int i = ia; i <= ib; ++i) {
+    const double dz = z[i + 1] - z[i];
+    S += w[i] * q[i] * dz;                                              // sputils.py:152
+    Sw += w[i] * dz;                                                    // sputils.py:157
+  }
+  const double Sa = w[ia] * q[ia] * (a - z[ia]);                        // sputils.py:154
+  const double Sb = w[ib] * q[ib] * (z[ib + 1] - b);                    // sputils.py:155
+  const double Swa = w[ia] * (a - z[ia]);                               // sputils.py:159
+  const double Swb = w[ib] * (z[ib + 1] - b);                           // sputils.py:160
+  return (S - Sa - Sb) / (Sw - Swa - Swb);                              // sputils.py:161
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
+  extern __shared__ __align__(16) double sm[];
+  const int nlev = a.g.nlev, nk = a.nk, ncol = a.g.ncol;
+  const int c = blockIdx.x;
+  double* ZfA = sm;              // [nlev] ascending heights  (Zf[::-1])
+  double* PfA = ZfA + nlev;      // [nlev] Pf[::-1]
+  double* zf = PfA + nlev;       // [nk]
+  double* t_d = zf + nk;         // 7 LES profiles [nk] each (spcpl.py:471-477)
+  double* qt_d = t_d + nk;
+  double* ql_d = qt_d + nk;
+  double* qlw_d = ql_d + nk;
+  double* qli_d = qlw_d + nk;
+  double* u_d = qli_d + nk;
+  double* v_d = u_d + nk;
+  double* rho = v_d + nk;        // [nk]   (conservative only)
+  double* ZhD = rho + nk;        // [nlev+1] descending half-level heights (conservative only)
+  int* cslab = reinterpret_cast<int*>(ZhD + nlev + 1);  // [nlev]
+  __shared__ int s_start;
+
+  const size_t b = (size_t)c * nlev, bh = (size_t)c * (nlev + 1);
+  const double zs = ld<T>(a.g.Zghalf, bh + nlev);
+  const spc_gcm_tend& o = a.o;
+  const size_t pfs = (size_t)ncol * nk;
+
+  for (int l = threadIdx.x; l < nlev; l += kThreads) {
+    ZfA[nlev - 1 - l] = (ld<T>(a.g.Zgfull, b + l) - zs) / grav;         // les.gcm_Zf, spcpl.py:198,390
+    PfA[nlev - 1 - l] = ld<T>(a.g.Pfull, b + l);
+    cslab[l] = 0;
+  }
+  if (a.conservative)
+    for (int l = threadIdx.x; l <= nlev; l += kThreads) ZhD[l] = (ld<T>(a.g.Zghalf, bh + l) - zs) / grav;
+  for (int k = threadIdx.x; k < nk; k += kThreads) {
+    const size_t i = (size_t)c * nk + k;
+    zf[k] = __ldg(a.zf + k);
+    const double ql = __ldg(a.les.prof + SPC_QL * pfs + i);
+    const double qli = ld<T>(a.les.QL_ice, i);
+    t_d[k] = ld<T>(a.les.T, i);
+    qt_d[k] = __ldg(a.les.prof + SPC_QT * pfs + i);
+    ql_d[k] = ql;
+    qlw_d[k] = ql - qli;                                                // spcpl.py:402
+    qli_d[k] = qli;
+    u_d[k] = __ldg(a.les.prof + SPC_U * pfs + i);
+    v_d[k] = __ldg(a.les.prof + SPC_V * pfs + i);
+    if (a.conservative) rho[k] = ld<T>(a.les.Rhobf, i);
+  }
+  __syncthreads();
+
+  // diagnostic temperature on LES levels, spcpl.py:408-409
+  if (o.t || o.bracket_pf) {
+    for (int k = threadIdx.x; k < nk; k += kThreads) {
+      const size_t i = (size_t)c * nk + k;
+      const int j = upper_bound(ZfA, nlev, zf[k]) - 1;
+      if (o.bracket_pf) o.bracket_pf[i] = j;
+      if (o.t) {
+        const double pf = interp_at(ZfA, PfA, nlev, zf[k], j);
+        const double thl_k = __ldg(a.les.prof + SPC_THL * pfs + i);
+        st<T>(o.t, i, thl_k * pow(pf / pref0, kExp) + rlv * ql_d[k] / cp);
+      }
+    }
+  }
+
+  // projected cloud cover per GCM slab from the K1 bit mask: slab r = LES levels
+  // [idx[r-1], idx[r]); count the horizontal points with any cloudy cell (spcpl.py:28,765)
+  const bool from_mask = (a.les.A == nullptr) && a.les.mask && a.les.slab_idx;
+  if (from_mask) {
+    const int mw = a.mask_words;
+    const uint32_t* m = a.les.mask + (size_t)c * nk * mw;
+    const int32_t* idx = a.les.slab_idx + b;
+    for (int w = threadIdx.x; w < mw; w += kThreads) {
+      int k0 = 0;
+      for (int r = 0; r < nlev && k0 < nk; ++r) {
+        const int k1 = min(max(__ldg(idx + r), k0), nk);
+        uint32_t acc = 0;
+        for (int k = k0; k < k1; ++k) acc |= __ldg(m + (size_t)k * mw + w);
+        if (acc) atomicAdd(&cslab[r], __popc(acc));
+        k0 = k1;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    // start_index = searchsorted(-Zf, -h[-1]) (spcpl.py:498): GCM levels strictly above the LES top.
+    // -Zf ascending <=> ZfA descending index; count of Zf > h_top = nlev - upper_bound(ZfA, h_top)
+    s_start = nlev - upper_bound(ZfA, nlev, zf[nk - 1]);
+    if (o.start_index) o.start_index[c] = s_start;
+  }
+  __syncthreads();
+
+  const double npts = (double)a.les.nx * (double)a.les.ny;
+  const double zh_top = a.zh ? __ldg(a.zh + nk - 1) : 0.0;
+  for (int l = threadIdx.x; l < nlev; l += kThreads) {
+    const size_t i = b + l;
+    const int r = nlev - 1 - l;                  // ascending slab index of GCM level l
+    double A_d;                                  // profile["A"][::-1], spcpl.py:404
+    if (a.les.A) A_d = ld<T>(a.les.A, b + r);
+    else if (from_mask) A_d = (double)cslab[r] / npts;
+    else A_d = 0.0;
+    if (o.cntslab) o.cntslab[i] = from_mask ? cslab[l] : -1;   // ascending order, as get_cloudfraction returns
+    st<T>(o.A_d, i, A_d);
+    const double x = ZfA[r];                     // Zf[l]
+    double tl, qtl, qll, qlwl, qlil, ul, vl;
+    if (!a.conservative) {                       // spcpl.py:468-477
+      const int j = upper_bound(zf, nk, x) - 1;
+      if (o.bracket) o.bracket[i] = j;
+      tl = interp_at(zf, t_d, nk, x, j);
+      qtl = interp_at(zf, qt_d, nk, x, j);
+      qll = interp_at(zf, ql_d, nk, x, j);
+      qlwl = interp_at(zf, qlw_d, nk, x, j);
+      qlil = interp_at(zf, qli_d, nk, x, j);
+      ul = interp_at(zf, u_d, nk, x, j);
+      vl = interp_at(zf, v_d, nk, x, j);
+    } else {                                     // spcpl.py:479-488 -> sputils.interp_c (sputils.py:173-189)
+      tl = qtl = qll = qlwl = qlil = ul = vl = 0.0;
+      if (o.bracket) o.bracket[i] = -2;
+      if (ZhD[l] < zh_top) {                     // sputils.py:187
+        const double lo = ZhD[l + 1], hi = ZhD[l];
+        tl = integral_w(lo, hi, a.zh, nk, t_d, rho);
+        qtl = integral_w(lo, hi, a.zh, nk, qt_d, rho);
+        qll = integral_w(lo, hi, a.zh, nk, ql_d, rho);
+        qlwl = integral_w(lo, hi, a.zh, nk, qlw_d, rho);
+        qlil = integral_w(lo, hi, a.zh, nk, qli_d, rho);
+        ul = integral_w(lo, hi, a.zh, nk, u_d, rho);
+        vl = integral_w(lo, hi, a.zh, nk, v_d, rho);
+      }
+    }
+    const double ft = a.dt;                      // spcpl.py:427
+    double f[SPC_NTEND];
+    f[SPC_F_T] = a.factor * (tl - ld<T>(a.g.T, i)) / ft;                 // spcpl.py:518
+    f[SPC_F_SH] = a.factor * ((qtl - qll) - ld<T>(a.g.SH, i)) / ft;      // spcpl.py:519
+    f[SPC_F_QL] = a.factor * (qlwl - ld<T>(a.g.QL, i)) / ft;             // spcpl.py:520
+    f[SPC_F_QI] = a.factor * (qlil - ld<T>(a.g.QI, i)) / ft;             // spcpl.py:521
+    f[SPC_F_U] = a.factor * (ul - ld<T>(a.g.U, i)) / ft;                 // spcpl.py:524
+    f[SPC_F_V] = a.factor * (vl - ld<T>(a.g.V, i)) / ft;                 // spcpl.py:525
+    f[SPC_F_A] = a.factor * (A_d - ld<T>(a.g.A, i)) / ft;                // spcpl.py:526
+    const bool above = l < s_start;              // spcpl.py:527-533: f[0:start_index] *= 0
+#pragma unroll
+    for (int n = 0; n < SPC_NTEND; ++n)
+      st<T>(o.tend, ((size_t)c * SPC_NTEND + n) * nlev + l, above ? f[n] * 0.0 : f[n]);
+  }
+}
+
+// ------------------------------------------------------------------- sputils batch helpers
+template <typename T>
+__global__ void interp_kernel(const T* x, int x_batched, const T* xp, const T* fp, int nx, int np, T* out, int32_t* br) {
+  extern __shared__ __align__(16) double sm[];
+  double* sxp = sm;
+  double* sfp = sm + np;
+  const int bidx = blockIdx.x;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    sxp[i] = (double)xp[(size_t)bidx * np + i];
+    sfp[i] = (double)fp[(size_t)bidx * np + i];
+  }
+  __syncthreads();
+  const T* xr = x + (x_batched ? (size_t)bidx * nx : 0);
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+    const double xv = (double)xr[i];
+    const int j = upper_bound(sxp, np, xv) - 1;
+    if (br) br[(size_t)bidx * nx + i] = j;
+    if (out) out[(size_t)bidx * nx + i] = (T)interp_at(sxp, sfp, np, xv, j);
+  }
+}
+
+template <typename T>
+__global__ void searchsorted_kernel(const T* a, const T* v, int v_batched, int na, int nv, int right, int32_t* out) {
+  extern __shared__ __align__(16) double sm[];
+  const int bidx = blockIdx.x;
+  for (int i = threadIdx.x; i < na; i += blockDim.x) sm[i] = (double)a[(size_t)bidx * na + i];
+  __syncthreads();
+  const T* vr = v + (v_batched ? (size_t)bidx * nv : 0);
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const double x = (double)vr[i];
+    out[(size_t)bidx * nv + i] = right ? upper_bound(sm, na, x) : lower_bound(sm, na, x);
+  }
+}
+
+template <typename T>
+__global__ void exner_kernel(const T* p, size_t n, double e, T* out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (T)pow((double)p[i] / pref0, e);
+}
+
+int check_gcm(const spc_gcm_cols* g, int couple_surface, const char* who) {
+  SPC_REQUIRE(g != nullptr, SPC_ERR_ARG, "%s: gcm is NULL", who);
+  SPC_REQUIRE(g->ncol >= 0 && g->nlev >= 2, SPC_ERR_ARG, "%s: bad shape ncol=%d nlev=%d", who, g->ncol, g->nlev);
+  SPC_REQUIRE(g->dtype == SPC_F32 || g->dtype == SPC_F64, SPC_ERR_ARG, "%s: bad dtype %d", who, g->dtype);
+  if (g->ncol == 0) return SPC_OK;
+  SPC_REQUIRE(g->U && g->V && g->T && g->SH && g->QL && g->QI && g->Pfull && g->A && g->Zgfull && g->Phalf && g->Zghalf,
+              SPC_ERR_ARG, "%s: a GCM profile pointer is NULL", who);
+  if (couple_surface)
+    SPC_REQUIRE(g->Z0M && g->Z0H && g->QLflux && g->QIflux && g->SHflux && g->TSflux, SPC_ERR_ARG,
+                "%s: couple_surface set but a surface field pointer is NULL", who);
+  return SPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spc_gcm_to_les(spc_handle h, const spc_gcm_cols* gcm, const double* zf, const double* zh, int nk,
+                   const double* les_prof, const void* ps_les, double dt, double factor, int couple_surface,
+                   const spc_les_forcing* out, void* stream) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  rc = check_gcm(gcm, couple_surface, "spc_gcm_to_les");
+  if (rc) return rc;
+  SPC_REQUIRE(zf && out && nk >= 1, SPC_ERR_ARG, "spc_gcm_to_les: zf/out NULL or nk < 1");
+  SPC_REQUIRE(dt != 0.0, SPC_ERR_ARG, "spc_gcm_to_les: dt must be non-zero");
+  SPC_REQUIRE(!(out->f_ps && !ps_les), SPC_ERR_ARG, "spc_gcm_to_les: f_ps requested but ps_les is NULL");
+  SPC_REQUIRE(!(out->slab_idx && !zh), SPC_ERR_ARG, "spc_gcm_to_les: slab_idx requested but zh is NULL");
+  SPC_REQUIRE(!((out->f_u || out->f_v || out->f_thl || out->f_qt || out->f_ql) && !les_prof), SPC_ERR_ARG,
+              "spc_gcm_to_les: forcings requested but les_prof is NULL");
+  if (gcm->ncol == 0) return SPC_OK;
+  const size_t smem = (size_t)6 * gcm->nlev * sizeof(double);
+  SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_gcm_to_les: nlev=%d too large", gcm->nlev);
+  spc::DeviceGuard guard(h->device);
+  K2Args a;
+  a.g = to_ptrs(gcm);
+  a.zf = zf; a.zh = zh; a.les_prof = les_prof; a.ps_les = ps_les;
+  a.o = *out;
+  a.dt = dt; a.factor = factor; a.nk = nk; a.couple_surface = couple_surface;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gcm->dtype == SPC_F32) gcm_to_les_kernel<float><<<gcm->ncol, kThreads, smem, st>>>(a);
+  else gcm_to_les_kernel<double><<<gcm->ncol, kThreads, smem, st>>>(a);
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, const double* zh, int nk,
+                   const spc_les_prof* les, double dt, double factor, int conservative, const spc_gcm_tend* out,
+                   void* stream) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  rc = check_gcm(gcm, 0, "spc_les_to_gcm");
+  if (rc) return rc;
+  SPC_REQUIRE(zf && les && out && nk >= 1, SPC_ERR_ARG, "spc_les_to_gcm: zf/les/out NULL or nk < 1");
+  SPC_REQUIRE(dt != 0.0, SPC_ERR_ARG, "spc_les_to_gcm: dt must be non-zero");
+  SPC_REQUIRE(out->tend != nullptr, SPC_ERR_ARG, "spc_les_to_gcm: out->tend is NULL");
+  SPC_REQUIRE(les->prof && les->QL_ice && les->T, SPC_ERR_ARG, "spc_les_to_gcm: a LES profile pointer is NULL");
+  SPC_REQUIRE(!(conservative && (!les->Rhobf || !zh)), SPC_ERR_ARG,
+              "spc_les_to_gcm: conservative coarsening needs Rhobf and zh");
+  int mw = 0;
+  if (!les->A && les->mask) {
+    SPC_REQUIRE(les->slab_idx != nullptr, SPC_ERR_ARG, "spc_les_to_gcm: mask given without slab_idx");
+    SPC_REQUIRE(les->nx > 0 && les->ny > 0, SPC_ERR_ARG, "spc_les_to_gcm: mask given without nx, ny");
+    const size_t per_col = spc_mask_words_per_column(les->vol_dtype, les->layout, les->nx, les->ny, nk);
+    SPC_REQUIRE(per_col > 0, SPC_ERR_UNSUPPORTED, "spc_les_to_gcm: no cloud mask format for this layout/shape");
+    mw = (int)(per_col / nk);
+  }
+  if (gcm->ncol == 0) return SPC_OK;
+  const size_t smem = ((size_t)2 * gcm->nlev + (size_t)9 * nk + gcm->nlev + 1) * sizeof(double) + (size_t)gcm->nlev * sizeof(int);
+  SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_les_to_gcm: nlev=%d, nk=%d too large", gcm->nlev, nk);
+  spc::DeviceGuard guard(h->device);
+  K3Args a;
+  a.g = to_ptrs(gcm);
+  a.zf = zf; a.zh = zh; a.les = *les; a.o = *out;
+  a.dt = dt; a.factor = factor; a.nk = nk; a.conservative = conservative; a.mask_words = mw;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gcm->dtype == SPC_F32) les_to_gcm_kernel<float><<<gcm->ncol, kThreads, smem, st>>>(a);
+  else les_to_gcm_kernel<double><<<gcm->ncol, kThreads, smem, st>>>(a);
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int spc_interp(spc_handle h, int dtype, const void* x, int x_batched, const void* xp, const void* fp, int nb, int nx,
+               int np, void* out, int32_t* bracket, void* stream) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  SPC_REQUIRE(dtype == SPC_F32 || dtype == SPC_F64, SPC_ERR_ARG, "spc_interp: bad dtype %d", dtype);
+  SPC_REQUIRE(nb >= 0 && nx >= 0 && np >= 1, SPC_ERR_ARG, "spc_interp: bad shape nb=%d nx=%d np=%d", nb, nx, np);
+  if (nb == 0 || nx == 0) return SPC_OK;
+  SPC_REQUIRE(x && xp && fp && (out || bracket), SPC_ERR_ARG, "spc_interp: NULL pointer");
+  const size_t smem = (size_t)2 * np * sizeof(double);
+  SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_interp: np=%d too large", np);
+  spc::DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SPC_F32)
+    interp_kernel<float><<<nb, kThreads, smem, st>>>((const float*)x, x_batched, (const float*)xp, (const float*)fp, nx, np,
+                                                    (float*)out, bracket);
+  else
+    interp_kernel<double><<<nb, kThreads, smem, st>>>((const double*)x, x_batched, (const double*)xp, (const double*)fp, nx,
+                                                     np, (double*)out, bracket);
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int spc_searchsorted(spc_handle h, int dtype, const void* a, const void* v, int v_batched, int nb, int na, int nv,
+                     int side_right, int32_t* out, void* stream) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  SPC_REQUIRE(dtype == SPC_F32 || dtype == SPC_F64, SPC_ERR_ARG, "spc_searchsorted: bad dtype %d", dtype);
+  SPC_REQUIRE(nb >= 0 && na >= 0 && nv >= 0, SPC_ERR_ARG, "spc_searchsorted: bad shape");
+  if (nb == 0 || nv == 0) return SPC_OK;
+  SPC_REQUIRE(v && out && (a || na == 0), SPC_ERR_ARG, "spc_searchsorted: NULL pointer");
+  const size_t smem = (size_t)std::max(na, 1) * sizeof(double);
+  SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_searchsorted: na=%d too large", na);
+  spc::DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SPC_F32)
+    searchsorted_kernel<float><<<nb, kThreads, smem, st>>>((const float*)a, (const float*)v, v_batched, na, nv, side_right, out);
+  else
+    searchsorted_kernel<double><<<nb, kThreads, smem, st>>>((const double*)a, (const double*)v, v_batched, na, nv, side_right,
+                                                           out);
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int spc_exner(spc_handle h, int dtype, const void* p, size_t n, int inverse, void* out, void* stream) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  SPC_REQUIRE(dtype == SPC_F32 || dtype == SPC_F64, SPC_ERR_ARG, "spc_exner: bad dtype %d", dtype);
+  if (n == 0) return SPC_OK;
+  SPC_REQUIRE(p && out, SPC_ERR_ARG, "spc_exner: NULL pointer");
+  spc::DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (int)std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)h->num_sms * 8);
+  const double e = inverse ? kIExp : kExp;
+  if (dtype == SPC_F32) exner_kernel<float><<<grid, kThreads, 0, st>>>((const float*)p, n, e, (float*)out);
+  else exner_kernel<double><<<grid, kThreads, 0, st>>>((const double*)p, n, e, (double*)out);
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,420 @@
+// K1 slab_reduce: horizontal slab means of the five LES volumes + above-threshold ql count/mask.
+//
+// Replaces the LES-side reductions the reference requests in spcpl.get_les_profiles
+// (splib/spcpl.py:747-759) and les.get_cloudfraction (spcpl.py:28,765). HBM-bound: every volume
+// byte is read exactly once; algorithmic bytes = 5*nx*ny*nk*sizeof(T) per column.
+//
+// Fast path (KJI layout, slab bytes % 16 == 0): persistent grid, one CTA per SM, every WARP owns a
+// private ring of NST shared-memory stages fed by 1-D TMA bulk copies (cp.async.bulk +
+// mbarrier complete_tx). Lane 0 keeps NST chunks in flight; the warp reduces a landed chunk with
+// conflict-free 128-bit LDS, accumulating in float64 (so the mean is order-insensitive to ~1e-16),
+// and finishes a slab with a shuffle butterfly. No block-wide barriers, no atomics, fixed order.
+#include "spc_common.cuh"
+
+namespace {
+
+constexpr int kWarps = 16;      // warps per CTA (one CTA per SM)
+constexpr int kChunk = 4096;    // bytes per TMA bulk copy / ring stage
+constexpr int kStages = 3;      // ring depth per warp -> 16*3*4 KB = 192 KB in flight per SM
+constexpr uint32_t kFull = 0xffffffffu;
+
+struct K1Args {
+  const void *v0, *v1, *v2, *v3, *v4;  // THL,QT,QL,U,V (named members: no local-memory copy for vol[f])
+  double* prof;
+  int32_t* cnt;
+  uint32_t* mask;
+  double thr;
+  long long per_field;  // ncol*nk slabs per field
+  long long total;      // 5*ncol*nk
+  int S;                // elements per slab
+  int slab_bytes;
+  int nch;              // chunks per slab
+};
+
+__device__ __forceinline__ const void* field_ptr(const K1Args& a, int f) {
+  return f == 0 ? a.v0 : f == 1 ? a.v1 : f == 2 ? a.v2 : f == 3 ? a.v3 : a.v4;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// One lane's share of a landed chunk: 16-byte vectors lane, lane+32, ... of `nvec`.
+template <typename T, bool QL>
+__device__ __forceinline__ void consume(const uint8_t* buf, int nvec, int lane, double (&acc)[4], int& cnt,
+                                        uint32_t& bits, double thr) {
+  constexpr int kIter = kChunk / 16 / 32;  // 8
+  if constexpr (sizeof(T) == 4) {
+    const float4* b = reinterpret_cast<const float4*>(buf);
+    float4 v[kIter];
+    if (nvec == kChunk / 16) {
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) v[it] = b[it * 32 + lane];
+    } else {
+#pragma unroll
+      for (int it = 0; it < kIter; ++it)
+        v[it] = (it * 32 + lane < nvec) ? b[it * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+      double d0 = (double)v[it].x, d1 = (double)v[it].y, d2 = (double)v[it].z, d3 = (double)v[it].w;
+      acc[0] += d0;
+      acc[1] += d1;
+      acc[2] += d2;
+      acc[3] += d3;
+      if constexpr (QL) {
+        // padding lanes hold 0.0 and must not count when thr < 0
+        bool in = (nvec == kChunk / 16) || (it * 32 + lane < nvec);
+        uint32_t m = (uint32_t)(in && d0 > thr) | ((uint32_t)(in && d1 > thr) << 1) |
+                     ((uint32_t)(in && d2 > thr) << 2) | ((uint32_t)(in && d3 > thr) << 3);
+        cnt += __popc(m);
+        bits |= m << (it * 4);
+      }
+    }
+  } else {
+    const double2* b = reinterpret_cast<const double2*>(buf);
+    double2 v[kIter];
+    if (nvec == kChunk / 16) {
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) v[it] = b[it * 32 + lane];
+    } else {
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) v[it] = (it * 32 + lane < nvec) ? b[it * 32 + lane] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+      acc[(2 * it) & 3] += v[it].x;
+      acc[(2 * it + 1) & 3] += v[it].y;
+      if constexpr (QL) {
+        bool in = (nvec == kChunk / 16) || (it * 32 + lane < nvec);
+        uint32_t m = (uint32_t)(in && v[it].x > thr) | ((uint32_t)(in && v[it].y > thr) << 1);
+        cnt += __popc(m);
+        bits |= m << (it * 2);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32, 1) slab_reduce_tma_kernel(const K1Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // [kWarps][kStages][kChunk] data, then [kWarps][kStages] mbarriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarps * kStages * kChunk);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* wbuf = smem + (size_t)warp * kStages * kChunk;
+  const uint32_t wbuf_s = smem_u32(wbuf);
+  const uint32_t wbar_s = smem_u32(bars + warp * kStages);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(wbar_s + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  const long long nwarps = (long long)gridDim.x * kWarps;
+  const long long gw = (long long)blockIdx.x * kWarps + warp;
+  if (gw >= a.total) return;
+  const long long nslab = (a.total - gw + nwarps - 1) / nwarps;  // slabs gw, gw+nwarps, ...
+  const long long nq = nslab * a.nch;                              // chunks this warp streams
+  const uint64_t pol = l2_evict_first_policy();
+
+  // producer state (lane 0): next chunk to issue
+  long long pi = 0;  // slab ordinal
+  int pj = 0;        // chunk within slab
+  auto issue = [&](int stage) {
+    const long long g = gw + pi * nwarps;
+    const int f = (int)(g / a.per_field);
+    const long long rem = g - (long long)f * a.per_field;
+    const uint8_t* src = static_cast<const uint8_t*>(field_ptr(a, f)) + (size_t)rem * a.slab_bytes + (size_t)pj * kChunk;
+    const int bytes = min(kChunk, a.slab_bytes - pj * kChunk);
+    const uint32_t bar = wbar_s + 8 * stage;
+    mbar_arrive_expect_tx(bar, (uint32_t)bytes);
+    tma_bulk_g2s(wbuf_s + stage * kChunk, src, (uint32_t)bytes, bar, pol);
+    if (++pj == a.nch) {
+      pj = 0;
+      ++pi;
+    }
+  };
+  if (lane == 0) {
+    const int pre = (int)min((long long)kStages, nq);
+    for (int s = 0; s < pre; ++s) issue(s);
+  }
+
+  int stage = 0;
+  uint32_t parity = 0;
+  long long q = 0;
+  for (long long i = 0; i < nslab; ++i) {
+    const long long g = gw + i * nwarps;
+    const int f = (int)(g / a.per_field);
+    const long long rem = g - (long long)f * a.per_field;  // = c*nk + k
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int cnt = 0;
+    const bool is_ql = (f == SPC_QL) && (a.cnt != nullptr || a.mask != nullptr);
+    for (int j = 0; j < a.nch; ++j, ++q) {
+      const uint32_t bar = wbar_s + 8 * stage;
+      while (!mbar_try_wait(bar, parity)) {
+      }
+      const int bytes = min(kChunk, a.slab_bytes - j * kChunk);
+      const uint8_t* buf = wbuf + stage * kChunk;
+      uint32_t bits = 0;
+      if (is_ql) {
+        consume<T, true>(buf, bytes >> 4, lane, acc, cnt, bits, a.thr);
+        if (a.mask) a.mask[((size_t)rem * a.nch + j) * 32 + lane] = bits;
+      } else {
+        consume<T, false>(buf, bytes >> 4, lane, acc, cnt, bits, a.thr);
+      }
+      __syncwarp();  // every lane is done reading this stage before it is refilled
+      if (lane == 0 && q + kStages < nq) issue(stage);
+      if (++stage == kStages) {
+        stage = 0;
+        parity ^= 1;
+      }
+    }
+    double s = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+    if (is_ql && a.cnt) {
+      int c = warp_sum(cnt);
+      if (lane == 0) a.cnt[rem] = c;
+    }
+    if (lane == 0) a.prof[g] = s / (double)a.S;
+  }
+}
+
+// Generic KJI path: any slab size / alignment. One warp per slab, scalar read-only loads.
+template <typename T>
+__global__ void __launch_bounds__(256) slab_reduce_generic_kernel(const K1Args a) {
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int mw = (a.S + 31) >> 5;
+  for (long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < a.total; g += nwarps) {
+    const int f = (int)(g / a.per_field);
+    const long long rem = g - (long long)f * a.per_field;
+    const T* p = static_cast<const T*>(field_ptr(a, f)) + (size_t)rem * a.S;
+    const bool is_ql = (f == SPC_QL) && (a.cnt != nullptr || a.mask != nullptr);
+    double acc = 0.0;
+    int cnt = 0;
+    for (int base = 0; base < a.S; base += 32) {
+      const int e = base + lane;
+      const bool in = e < a.S;
+      const double v = in ? (double)__ldg(p + e) : 0.0;
+      acc += v;
+      if (is_ql) {
+        const uint32_t w = __ballot_sync(kFull, in && v > a.thr);
+        cnt += __popc(w);
+        if (a.mask && lane == 0) a.mask[(size_t)rem * mw + (base >> 5)] = w;
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      a.prof[g] = acc / (double)a.S;
+      if (is_ql && a.cnt) a.cnt[rem] = cnt;
+    }
+  }
+}
+
+// IJK layout ([ncol][nx][ny][nk], k fastest): one CTA per (field, column); thread (r, kk) walks the
+// horizontal points r, r+R, ... of its level(s) kk with coalesced loads along k, then the R partial
+// sums per level are combined through shared memory in a fixed order.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(1024) slab_reduce_ijk_kernel(const K1Args a, int nk, int ncol, int nkv, int R) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  double* ssum = reinterpret_cast<double*>(smem);                  // [R][nk]
+  int* scnt = reinterpret_cast<int*>(ssum + (size_t)R * nk);       // [R][nk]
+  const int f = blockIdx.x / ncol, c = blockIdx.x - f * ncol;
+  const int kk = threadIdx.x % nkv, r = threadIdx.x / nkv;
+  const bool is_ql = (f == SPC_QL) && a.cnt != nullptr;
+  const T* p = static_cast<const T*>(field_ptr(a, f)) + (size_t)c * a.S * nk;
+  double acc[VEC];
+  int cnt[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    acc[v] = 0.0;
+    cnt[v] = 0;
+  }
+  if (r < R) {
+    for (int row = r; row < a.S; row += R) {
+      if constexpr (VEC == 1) {
+        const double d = (double)__ldg(p + (size_t)row * nk + kk);
+        acc[0] += d;
+        cnt[0] += (d > a.thr);
+      } else if constexpr (sizeof(T) == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p + (size_t)row * nk) + kk);
+        const double d[4] = {(double)q.x, (double)q.y, (double)q.z, (double)q.w};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          acc[v] += d[v];
+          cnt[v] += (d[v] > a.thr);
+        }
+      } else {
+        const double2 q = __ldg(reinterpret_cast<const double2*>(p + (size_t)row * nk) + kk);
+        acc[0] += q.x;
+        acc[1] += q.y;
+        cnt[0] += (q.x > a.thr);
+        cnt[1] += (q.y > a.thr);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      ssum[(size_t)r * nk + kk * VEC + v] = acc[v];
+      scnt[(size_t)r * nk + kk * VEC + v] = cnt[v];
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nk; k += blockDim.x) {
+    double s = 0.0;
+    int n = 0;
+    for (int rr = 0; rr < R; ++rr) {
+      s += ssum[(size_t)rr * nk + k];
+      n += scnt[(size_t)rr * nk + k];
+    }
+    a.prof[((size_t)f * ncol + c) * nk + k] = s / (double)a.S;
+    if (is_ql) a.cnt[(size_t)c * nk + k] = n;
+  }
+}
+
+bool fast_path(int dtype, long long S) {
+  const long long slab_bytes = S * (dtype == SPC_F32 ? 4 : 8);
+  return slab_bytes % 16 == 0 && slab_bytes >= 1024;
+}
+
+template <typename T>
+int launch_kji(spc_handle h, const K1Args& a, bool fast, cudaStream_t st) {
+  if (fast) {
+    const size_t smem = (size_t)kWarps * kStages * kChunk + (size_t)kWarps * kStages * 8;
+    static thread_local int configured_dev = -1;
+    if (configured_dev != h->device) {
+      SPC_CUDA(cudaFuncSetAttribute(slab_reduce_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_dev = h->device;
+    }
+    const long long want = (a.total + kWarps - 1) / kWarps;
+    const int grid = (int)std::min<long long>(h->num_sms, std::max<long long>(want, 1));
+    slab_reduce_tma_kernel<T><<<grid, kWarps * 32, smem, st>>>(a);
+  } else {
+    const long long want = (a.total + 7) / 8;
+    const int grid = (int)std::min<long long>((long long)h->num_sms * 8, std::max<long long>(want, 1));
+    slab_reduce_generic_kernel<T><<<grid, 256, 0, st>>>(a);
+  }
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+template <typename T>
+int launch_ijk(spc_handle h, const K1Args& a, int ncol, int nk, cudaStream_t st) {
+  constexpr int V = 16 / sizeof(T);
+  bool vec = (nk % V == 0);
+  const void* vols[SPC_NFIELDS] = {a.v0, a.v1, a.v2, a.v3, a.v4};
+  for (int f = 0; f < SPC_NFIELDS && vec; ++f) vec = (reinterpret_cast<uintptr_t>(vols[f]) % 16 == 0);
+  const int nkv = vec ? nk / V : nk;
+  SPC_REQUIRE(nkv <= 1024, SPC_ERR_UNSUPPORTED, "spc_slab_reduce: nk=%d too large for the IJK layout kernel", nk);
+  int R = std::max(1, std::min(a.S, 512 / nkv));
+  size_t smem = (size_t)R * nk * (sizeof(double) + sizeof(int));
+  while (smem > 48 * 1024 && R > 1) {
+    --R;
+    smem = (size_t)R * nk * (sizeof(double) + sizeof(int));
+  }
+  SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_slab_reduce: nk=%d too large for the IJK layout kernel", nk);
+  const int threads = ((nkv * R + 31) / 32) * 32;
+  const int grid = SPC_NFIELDS * ncol;
+  if (vec)
+    slab_reduce_ijk_kernel<T, V><<<grid, threads, smem, st>>>(a, nk, ncol, nkv, R);
+  else
+    slab_reduce_ijk_kernel<T, 1><<<grid, threads, smem, st>>>(a, nk, ncol, nkv, R);
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t spc_mask_words_per_column(int dtype, int layout, int nx, int ny, int nk) {
+  if (nx <= 0 || ny <= 0 || nk <= 0 || layout != SPC_LAYOUT_KJI) return 0;
+  const long long S = (long long)nx * ny;
+  if (fast_path(dtype, S)) {
+    const long long slab_bytes = S * (dtype == SPC_F32 ? 4 : 8);
+    return (size_t)((slab_bytes + kChunk - 1) / kChunk) * 32 * nk;
+  }
+  return (size_t)((S + 31) / 32) * nk;
+}
+
+int spc_slab_reduce(spc_handle h, const void* const vol[5], int dtype, int layout, int ncol, int nx, int ny, int nk,
+                    double ql_thresh, double* prof, int32_t* cnt, uint32_t* mask, void* stream) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  SPC_REQUIRE(vol && prof, SPC_ERR_ARG, "spc_slab_reduce: vol/prof is NULL");
+  SPC_REQUIRE(dtype == SPC_F32 || dtype == SPC_F64, SPC_ERR_ARG, "spc_slab_reduce: bad dtype %d", dtype);
+  SPC_REQUIRE(layout == SPC_LAYOUT_KJI || layout == SPC_LAYOUT_IJK, SPC_ERR_ARG, "spc_slab_reduce: bad layout %d", layout);
+  SPC_REQUIRE(ncol >= 0 && nx > 0 && ny > 0 && nk > 0, SPC_ERR_ARG, "spc_slab_reduce: bad shape ncol=%d nx=%d ny=%d nk=%d",
+              ncol, nx, ny, nk);
+  const long long S = (long long)nx * ny;
+  SPC_REQUIRE(S * (dtype == SPC_F32 ? 4 : 8) < (1ll << 31), SPC_ERR_UNSUPPORTED, "spc_slab_reduce: slab too large");
+  if (ncol == 0) return SPC_OK;
+  for (int f = 0; f < SPC_NFIELDS; ++f) SPC_REQUIRE(vol[f] != nullptr, SPC_ERR_ARG, "spc_slab_reduce: vol[%d] is NULL", f);
+  SPC_REQUIRE(!(layout == SPC_LAYOUT_IJK && mask), SPC_ERR_UNSUPPORTED,
+              "spc_slab_reduce: the cloud mask is only produced for the KJI layout");
+  spc::DeviceGuard guard(h->device);
+  K1Args a;
+  a.v0 = vol[0]; a.v1 = vol[1]; a.v2 = vol[2]; a.v3 = vol[3]; a.v4 = vol[4];
+  a.prof = prof;
+  a.cnt = cnt;
+  a.mask = mask;
+  a.thr = ql_thresh;
+  a.per_field = (long long)ncol * nk;
+  a.total = a.per_field * SPC_NFIELDS;
+  a.S = (int)S;
+  a.slab_bytes = (int)(S * (dtype == SPC_F32 ? 4 : 8));
+  a.nch = (a.slab_bytes + kChunk - 1) / kChunk;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (layout == SPC_LAYOUT_IJK) {
+    return dtype == SPC_F32 ? launch_ijk<float>(h, a, ncol, nk, st) : launch_ijk<double>(h, a, ncol, nk, st);
+  }
+  const bool fast = fast_path(dtype, S);
+  if (fast) {
+    for (int f = 0; f < SPC_NFIELDS; ++f)
+      SPC_REQUIRE(reinterpret_cast<uintptr_t>(vol[f]) % 16 == 0, SPC_ERR_ALIGN,
+                  "spc_slab_reduce: vol[%d] must be 16-byte aligned for the TMA bulk path", f);
+  }
+  return dtype == SPC_F32 ? launch_kji<float>(h, a, fast, st) : launch_kji<double>(h, a, fast, st);
+}
+
+}  // extern "C"

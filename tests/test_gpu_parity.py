@@ -1,0 +1,227 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs, and against the golden vectors produced by the unmodified reference.
+
+Gates: counts, bracket indices, slab indices, start_index: exact integer equality.
+Profiles / forcings / tendencies: max|a-b| / max|ref| <= 1e-6 (float64 mode), 1e-4 (float32 mode).
+"""
+import numpy as np
+import pytest
+
+import cases
+from conftest import GOLDEN_CASES, load_golden, relerr
+from oracle import numpy_batched as nb
+from sp_coupler_b200.constants import LES_FIELDS, TENDENCIES
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.float64: 1e-6, np.float32: 1e-4}
+FORCINGS = ("f_u", "f_v", "f_thl", "f_qt", "f_ql", "f_ps", "ql_ref", "z0m", "z0h", "wthl", "wqt")
+
+
+@pytest.fixture(scope="module")
+def cpl(cuda_device):
+    from sp_coupler_b200.coupler import Coupler
+    return Coupler(cuda_device)
+
+
+def n(t):
+    return t.detach().cpu().numpy()
+
+
+def check_step(case, ref, slab, frc, tnd, rtol, mask_expected=True):
+    for i, f in enumerate(LES_FIELDS):
+        assert relerr(n(slab["prof"][i]), ref["prof"][f]) <= min(rtol, 1e-12), f   # float64 accumulation
+    assert np.array_equal(n(slab["cnt"]), ref["cnt"])
+    assert np.array_equal(n(frc["slab_idx"]), ref["slab_idx"])
+    assert np.array_equal(n(frc["bracket"]), ref["forcings"]["bracket"])
+    for k in FORCINGS:
+        assert relerr(n(frc[k]), ref["forcings"][k]) <= rtol, k
+    for k, o in (("u", "u"), ("v", "v"), ("thl", "thl"), ("qt", "qt"), ("Tv", "Tv"), ("THL", "THL"), ("QT", "QT"),
+                 ("Zf", "Zf"), ("Zh", "Zh"), ("ps", "ps")):
+        assert relerr(n(frc[k]), ref["forcings"][o]) <= rtol, k
+    t = ref["tendencies"]
+    if mask_expected:
+        assert np.array_equal(n(tnd["cntslab"]), ref["cntslab"])
+    assert np.array_equal(n(tnd["start_index"]), t["start_index"])
+    assert np.array_equal(n(tnd["bracket"]), t["bracket"])
+    assert np.array_equal(n(tnd["bracket_pf"]), t["bracket_pf"])
+    for k in TENDENCIES:
+        assert relerr(n(tnd[k]), t[k]) <= rtol, k
+    assert relerr(n(tnd["t"]), t["t"]) <= rtol
+    assert relerr(n(tnd["A_d"]), t["A_d"]) <= rtol
+
+
+@pytest.mark.parametrize("ncol,nx,ny,nk,nlev,dtype", [
+    (2, 64, 64, 160, 19, np.float64),     # C1: T21 example shape
+    (4, 64, 64, 160, 91, np.float64),     # C2 shape (fp64 equivalence), reduced ncol
+    (4, 64, 64, 160, 91, np.float32),     # C3 shape, reduced ncol
+    (3, 32, 32, 160, 137, np.float32),    # C5 shape
+    (1, 256, 256, 20, 91, np.float32),    # C4 slab size (256 KB slabs span many TMA chunks)
+    (3, 8, 8, 20, 19, np.float64),        # spdummy-sized LES: generic (non-TMA) path
+    (2, 10, 10, 20, 19, np.float32),      # slab bytes not a multiple of 16: generic path
+    (2, 40, 40, 24, 91, np.float32),      # ragged: slab = 1 full + 1 partial TMA chunk
+    (2, 24, 20, 16, 19, np.float64),      # ragged float64 chunks
+])
+def test_coupling_step_matches_oracle(cpl, cuda_device, ncol, nx, ny, nk, nlev, dtype):
+    case = cases.host_case(ncol, nx, ny, nk, nlev, dtype)
+    ref = cases.oracle_step(case)
+    assert ref["cnt"].sum() > 0 and (ref["cnt"] == 0).any()      # non-trivial counts, exact zeros
+    d = cases.to_device(case, cuda_device)
+    slab, frc, tnd = cases.gpu_step(cpl, d)
+    check_step(case, ref, slab, frc, tnd, RTOL[dtype])
+    if dtype == np.float64:
+        # float64 mode is far tighter than the gate: only pow differs from numpy (<= 2 ulp)
+        for k in TENDENCIES:
+            assert relerr(n(tnd[k]), ref["tendencies"][k]) <= 1e-12, k
+        for k in FORCINGS:
+            assert relerr(n(frc[k]), ref["forcings"][k]) <= 1e-12, k
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_ijk_layout_matches_oracle(cpl, cuda_device, dtype):
+    case = cases.host_case(2, 16, 12, 160, 19, dtype, layout=1)
+    ref = cases.oracle_step(case)
+    d = cases.to_device(case, cuda_device)
+    slab = cpl.slab_reduce(d["vols"], layout="ijk", want_mask=False)
+    for i, f in enumerate(LES_FIELDS):
+        assert relerr(n(slab["prof"][i]), ref["prof"][f]) <= 1e-12, f
+    assert np.array_equal(n(slab["cnt"]), ref["cnt"])
+    # odd nk: scalar (non-vectorised) variant
+    case = cases.host_case(2, 6, 5, 21, 19, dtype, layout=1)
+    ref = cases.oracle_step(case)
+    d = cases.to_device(case, cuda_device)
+    slab = cpl.slab_reduce(d["vols"], layout="ijk", want_mask=False)
+    for i, f in enumerate(LES_FIELDS):
+        assert relerr(n(slab["prof"][i]), ref["prof"][f]) <= 1e-12, f
+    assert np.array_equal(n(slab["cnt"]), ref["cnt"])
+
+
+@pytest.mark.parametrize("thr", [-1.0, 0.0, 1e-5])
+def test_cloud_threshold_semantics(cpl, cuda_device, thr):
+    """strict '>' on the float64 value; a negative threshold must not count chunk padding."""
+    case = cases.host_case(2, 40, 40, 24, 19, np.float32)
+    ref = cases.oracle_step(case, ql_thresh=thr)
+    d = cases.to_device(case, cuda_device)
+    slab, frc, tnd = cases.gpu_step(cpl, d, ql_thresh=thr)
+    assert np.array_equal(n(slab["cnt"]), ref["cnt"])
+    assert np.array_equal(n(tnd["cntslab"]), ref["cntslab"])
+    if thr < 0:
+        assert (ref["cnt"] == 1600).all()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_profile_kernels_match_reference_golden(cpl, cuda_device, name):
+    """K2/K3 against outputs of the UNMODIFIED reference (tests/golden, oracle/make_golden.py)."""
+    import torch
+    c = load_golden(name)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    gcm = {k: t(v) for k, v in c["gcm"].items()}
+    zf, zh = t(c["zf"]), t(c["zh"])
+    prof = t(np.stack([c["les"][f] for f in LES_FIELDS]))
+    frc = cpl.gcm_to_les(gcm, zf, zh, prof, t(c["aux"]["PS"]), c["dt"], c["f_les"], True, diagnostics=True)
+    out = c["out"]
+    for k in FORCINGS:
+        assert relerr(n(frc[k]), out[k]) <= 1e-12, k
+    for k in ("Tv", "THL", "QT", "Zf"):
+        assert relerr(n(frc[k]), out[k]) <= 1e-12, k
+    assert np.array_equal(n(frc["Zh"]), out["gcm_Zh"])          # heights are bit-exact (IEEE sub, div)
+    assert np.array_equal(n(frc["Zf"]), out["gcm_Zf"])
+    assert np.array_equal(n(frc["slab_idx"]), out["slab_idx"])
+    aux = {k: t(v) for k, v in c["aux"].items()}
+    tnd = cpl.les_to_gcm(gcm, zf, zh, {"prof": prof}, aux, None, c["dt"], c["f_gcm"], A=t(c["A_les"]), diagnostics=True)
+    for k in TENDENCIES:
+        assert relerr(n(tnd[k]), out[k]) <= 1e-12, k
+    assert np.array_equal(n(tnd["start_index"]), out["start_index"])
+    assert relerr(n(tnd["t"]), out["t"]) <= 1e-12
+    assert np.array_equal(n(tnd["A_d"]), out["A_d"])
+
+
+def test_conservative_coarsening_matches_reference_golden(cpl, cuda_device):
+    """sputils.interp_c path (--conservative_coarsening), spcpl.py:479-488."""
+    import torch
+    c = load_golden("ref_L91_cons")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    gcm = {k: t(v) for k, v in c["gcm"].items()}
+    prof = t(np.stack([c["les"][f] for f in LES_FIELDS]))
+    aux = {k: t(v) for k, v in c["aux"].items()}
+    tnd = cpl.les_to_gcm(gcm, t(c["zf"]), t(c["zh"]), {"prof": prof}, aux, None, c["dt"], c["f_gcm"],
+                         conservative=True, A=t(c["A_les"]))
+    for k in TENDENCIES:
+        assert relerr(n(tnd[k]), c["out"][k]) <= 1e-6, k
+        assert relerr(n(tnd[k]), c["out"][k]) <= 1e-11, k      # only the summation order differs
+    assert np.array_equal(n(tnd["start_index"]), c["out"]["start_index"])
+
+
+def test_sputils_helpers(cpl, cuda_device):
+    import torch
+    rng = np.random.default_rng(11)
+    nb_, np_, nx = 5, 37, 160
+    xp = np.sort(rng.uniform(0, 4000, (nb_, np_)), axis=1)
+    fp = rng.normal(size=(nb_, np_))
+    x = np.concatenate([rng.uniform(-50, 4100, nx - 3), xp[0, [0, 5, -1]]])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    out, br = cpl.interp(t(x), t(xp), t(fp), want_bracket=True)
+    ref = np.stack([np.interp(x, xp[i], fp[i]) for i in range(nb_)])
+    assert np.array_equal(n(out), ref)                          # bit-exact in float64 (--fmad=false)
+    assert np.array_equal(n(br), np.stack([nb.bracket(x, xp[i]) for i in range(nb_)]))
+    for side in ("left", "right"):
+        ss = cpl.searchsorted(t(xp), t(x), side=side)
+        assert np.array_equal(n(ss), np.stack([np.searchsorted(xp[i], x, side=side) for i in range(nb_)]))
+    p = rng.uniform(1e3, 1.05e5, 1000)
+    assert relerr(n(cpl.exner(t(p))), nb.exner(p)) <= 1e-14
+    assert relerr(n(cpl.exner(t(p), inverse=True)), nb.iexner(p)) <= 1e-14
+    # the reference's own known-answer tests (splib/test/sputils_test.py:25-39)
+    a = 2.03947
+    e = n(cpl.exner(t(np.array([a * nb.pref0, nb.pref0, 12.03947 * nb.pref0]))))
+    ie = n(cpl.exner(t(np.array([12.03947 * nb.pref0])), inverse=True))
+    assert abs(np.log(e[0]) - np.log(a) * nb.rd / nb.cp) < 1e-10
+    assert abs(e[1] - 1) < 1e-10
+    assert abs(e[2] * ie[0] - 1) < 1e-10
+
+
+def test_cloud_fraction_index_mapping_kat(cpl, cuda_device):
+    """splib/test/spcpl_test.py:10-16: zh=(k+0.5)*200, Zh=[1e5,1e3,100,10,1,0] -> [0,0,1,5,20]."""
+    import os
+    import torch
+    import conftest
+    z = np.load(os.path.join(conftest.GOLDEN, "ref_kat.npz"))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    ss = n(cpl.searchsorted(t(z["cf_zh"][None, :]), t(z["cf_Zh"]), side="right"))[0]
+    assert ss[:-1][::-1].tolist() == [0, 0, 1, 5, 20]
+
+
+def test_set_les_state_bit_identical_to_host_generator(cpl, cuda_device):
+    import torch
+    from sp_coupler_b200 import synth
+    rng = np.random.default_rng(2)
+    for dtype, td in ((np.float32, torch.float32), (np.float64, torch.float64)):
+        for (ncol, nk, ny, nx) in ((3, 7, 8, 12), (2, 5, 3, 5)):
+            prof = rng.normal(300, 5, (ncol, nk))
+            sub = prof + 0.05 * rng.normal(size=(ncol, nk))
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+            v = n(cpl.set_les_state(t(prof), 0.1, 3, nx, ny, seed=42, col0=5, dtype=td))
+            assert np.array_equal(v, synth.les_state_volume(prof, 0.1, 3, nx, ny, seed=42, col0=5, dtype=dtype))
+            v = n(cpl.set_les_state(t(prof), 0.1, 1, nx, ny, seed=7, col0=0, sub=t(sub), clamp0=True, dtype=td))
+            h = synth.les_state_volume(prof, 0.1, 1, nx, ny, seed=7, col0=0, sub=sub, clamp0=True, dtype=dtype)
+            assert np.array_equal(v, h) and (v == 0).any() and (v > 0).any()
+
+
+def test_errors_are_loud(cpl, cuda_device):
+    import torch
+    case = cases.host_case(1, 8, 8, 20, 19, np.float32)
+    d = cases.to_device(case, cuda_device)
+    with pytest.raises((RuntimeError, ValueError, TypeError)):
+        cpl.slab_reduce([v.cpu() for v in d["vols"]])                       # CPU tensors are rejected
+    with pytest.raises(RuntimeError):
+        cpl.gcm_to_les(d["gcm"], d["zf"], d["zh"], None, d["aux"]["PS"], dt=0.0)   # dt == 0
+    bad = dict(d["gcm"])
+    bad["T"] = bad["T"].double()
+    with pytest.raises((RuntimeError, ValueError, TypeError)):
+        cpl.gcm_to_les(bad, d["zf"], d["zh"])
+
+
+def test_empty_batch(cpl, cuda_device):
+    import torch
+    vols = [torch.empty((0, 20, 8, 8), device=cuda_device) for _ in range(5)]
+    slab = cpl.slab_reduce(vols)
+    assert slab["prof"].shape == (5, 0, 20)
