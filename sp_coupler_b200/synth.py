@@ -214,3 +214,19 @@ def make_les_volumes(gcm, zf, nx, ny, seed=42, dtype=np.float32, col0=0):
     plan = les_volume_plan(gcm, zf, col0=col0)
     return {f: les_state_volume(p, amp, st, nx, ny, seed=seed, col0=col0, sub=sub, clamp0=cl, dtype=dtype)
             for f, (p, amp, st, sub, cl) in plan.items()}
+
+
+def device_les_volumes(cpl, gcm, zf, nx, ny, seed=42, dtype=None, col0=0):
+    """The same synthetic LES volumes as make_les_volumes(), generated on the device by the
+    spc_set_les_state kernel (bit-identical; used for configs too large to build on the host).
+    Returns the five [ncol][nk][ny][nx] tensors in LES_FIELDS order."""
+    import torch
+    dtype = dtype if dtype is not None else torch.float32
+    plan = les_volume_plan(gcm, zf, col0=col0)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(cpl.device)
+    out = []
+    for f in C.LES_FIELDS:
+        prof, amp, stream, sub, clamp0 = plan[f]
+        out.append(cpl.set_les_state(up(prof), amp, stream, nx, ny, seed=seed, col0=col0,
+                                     sub=None if sub is None else up(sub), clamp0=clamp0, dtype=dtype))
+    return out
