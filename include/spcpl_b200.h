@@ -145,6 +145,14 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
                    const spc_les_prof* les, double dt, double factor, int conservative,
                    const spc_gcm_tend* out, void* stream);
 
+/* les.get_cloudfraction(indices) (spcpl.py:28,765) on its own: projected cloudy-column count per
+ * GCM slab from the spc_slab_reduce mask. slab_idx [ncol][nlev] ascending (spc_gcm_to_les);
+ * cntslab int32 [ncol][nlev] and/or A = cntslab/(nx*ny) of out_dtype, both in ascending slab order
+ * (the order get_cloudfraction returns; the coupler reverses it, spcpl.py:28,404). */
+int spc_cloud_fraction(spc_handle h, const uint32_t* mask, const int32_t* slab_idx, int vol_dtype, int layout,
+                       int nx, int ny, int nk, int ncol, int nlev, int out_dtype,
+                       int32_t* cntslab, void* A, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * sputils.interp / sputils.searchsorted (sputils.py:82-91) over a batch of rows.
  *   x  [nb][nx] (x_batched != 0) or [nx] shared by all rows; xp, fp [nb][np], xp increasing.

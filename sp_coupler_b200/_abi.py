@@ -14,7 +14,7 @@ NFIELDS, NTEND = 5, 7
 
 # every symbol include/spcpl_b200.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = ["spc_abi_version", "spc_last_error", "spc_create", "spc_destroy", "spc_mask_words_per_column",
-           "spc_slab_reduce", "spc_gcm_to_les", "spc_les_to_gcm", "spc_interp", "spc_searchsorted", "spc_exner",
+           "spc_slab_reduce", "spc_gcm_to_les", "spc_les_to_gcm", "spc_cloud_fraction", "spc_interp", "spc_searchsorted", "spc_exner",
            "spc_set_les_state"]
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -69,6 +69,7 @@ def lib():
                                  C.POINTER(LesForcing), _vp]
     L.spc_les_to_gcm.argtypes = [_vp, C.POINTER(GcmCols), _vp, _vp, _i, C.POINTER(LesProf), _d, _d, _i,
                                  C.POINTER(GcmTend), _vp]
+    L.spc_cloud_fraction.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]
     L.spc_interp.argtypes = [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]
     L.spc_searchsorted.argtypes = [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]
     L.spc_exner.argtypes = [_vp, _i, _vp, C.c_size_t, _i, _vp, _vp]

@@ -228,6 +228,23 @@ class Coupler(object):
             res[n] = tend[:, i, :]
         return res
 
+    def cloud_fraction(self, slab, slab_idx, dtype=None):
+        """les.get_cloudfraction(indices) for all columns (spcpl.py:28,765): (A, cntslab) in ascending
+        slab order from the slab_reduce cloud mask."""
+        ncol, nlev = slab_idx.shape
+        nk = slab["prof"].shape[2]
+        dtype = dtype if dtype is not None else slab["dtype"]
+        self._chk(slab_idx, "slab_idx", torch.int32)
+        if slab.get("mask") is None:
+            raise ValueError("slab_reduce was run without want_mask")
+        A = self._empty((ncol, nlev), dtype)
+        cs = self._empty((ncol, nlev), torch.int32)
+        _abi.check(self._lib.spc_cloud_fraction(self._h, _ptr(slab["mask"]), _ptr(slab_idx), _DT[slab["dtype"]],
+                                                slab["layout"], slab["nx"], slab["ny"], nk, ncol, nlev, _DT[dtype],
+                                                _ptr(cs), _ptr(A), self._stream()), "spc_cloud_fraction")
+        self.launches += 1
+        return A, cs
+
     # ------------------------------------------------------------------ sputils helpers
     def interp(self, x, xp, fp, want_bracket=False):
         """numpy.interp over a batch of rows (sputils.py:82-86). x: [nx] or [nb,nx]; xp, fp: [nb,np]."""

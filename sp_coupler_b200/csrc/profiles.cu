@@ -166,6 +166,41 @@ __device__ double integral_w(double a, double b, const double* z, int n, const d
   return (S - Sa - Sb) / (Sw - Swa - Swb);                              // sputils.py:161
 }
 
+// Projected cloud cover per GCM slab from the K1 bit mask of one column: slab r = LES levels
+// [idx[r-1], idx[r]) (idx[-1] := 0, clipped to nk); cslab[r] += number of horizontal points with
+// any cloudy cell in the slab (les.get_cloudfraction(indices), spcpl.py:28,765). The mask layout
+// is opaque but identical for every level, so OR over k then popcount is layout-independent.
+// cslab must be zeroed by the caller; integer atomics in shared memory keep the result exact.
+__device__ __forceinline__ void project_cloud_mask(const uint32_t* m, const int32_t* idx, int mw, int nk, int nlev,
+                                                   int* cslab) {
+  for (int w = threadIdx.x; w < mw; w += blockDim.x) {
+    int k0 = 0;
+    for (int r = 0; r < nlev && k0 < nk; ++r) {
+      const int k1 = min(max(__ldg(idx + r), k0), nk);
+      uint32_t acc = 0;
+      for (int k = k0; k < k1; ++k) acc |= __ldg(m + (size_t)k * mw + w);
+      if (acc) atomicAdd(&cslab[r], __popc(acc));
+      k0 = k1;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) cloud_fraction_kernel(const uint32_t* mask, const int32_t* slab_idx, int mw,
+                                                                  int nk, int nlev, double npts, int32_t* cntslab, T* A) {
+  extern __shared__ __align__(16) double sm[];
+  int* cslab = reinterpret_cast<int*>(sm);
+  const int c = blockIdx.x;
+  for (int l = threadIdx.x; l < nlev; l += kThreads) cslab[l] = 0;
+  __syncthreads();
+  project_cloud_mask(mask + (size_t)c * nk * mw, slab_idx + (size_t)c * nlev, mw, nk, nlev, cslab);
+  __syncthreads();
+  for (int l = threadIdx.x; l < nlev; l += kThreads) {
+    if (cntslab) cntslab[(size_t)c * nlev + l] = cslab[l];
+    if (A) A[(size_t)c * nlev + l] = (T)((double)cslab[l] / npts);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
   extern __shared__ __align__(16) double sm[];
@@ -228,24 +263,9 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
     }
   }
 
-  // projected cloud cover per GCM slab from the K1 bit mask: slab r = LES levels
-  // [idx[r-1], idx[r]); count the horizontal points with any cloudy cell (spcpl.py:28,765)
+  // projected cloud cover per GCM slab from the K1 bit mask
   const bool from_mask = (a.les.A == nullptr) && a.les.mask && a.les.slab_idx;
-  if (from_mask) {
-    const int mw = a.mask_words;
-    const uint32_t* m = a.les.mask + (size_t)c * nk * mw;
-    const int32_t* idx = a.les.slab_idx + b;
-    for (int w = threadIdx.x; w < mw; w += kThreads) {
-      int k0 = 0;
-      for (int r = 0; r < nlev && k0 < nk; ++r) {
-        const int k1 = min(max(__ldg(idx + r), k0), nk);
-        uint32_t acc = 0;
-        for (int k = k0; k < k1; ++k) acc |= __ldg(m + (size_t)k * mw + w);
-        if (acc) atomicAdd(&cslab[r], __popc(acc));
-        k0 = k1;
-      }
-    }
-  }
+  if (from_mask) project_cloud_mask(a.les.mask + (size_t)c * nk * a.mask_words, a.les.slab_idx + b, a.mask_words, nk, nlev, cslab);
   if (threadIdx.x == 0) {
     // start_index = searchsorted(-Zf, -h[-1]) (spcpl.py:498): GCM levels strictly above the LES top.
     // -Zf ascending <=> ZfA descending index; count of Zf > h_top = nlev - upper_bound(ZfA, h_top)
@@ -425,6 +445,30 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (gcm->dtype == SPC_F32) les_to_gcm_kernel<float><<<gcm->ncol, kThreads, smem, st>>>(a);
   else les_to_gcm_kernel<double><<<gcm->ncol, kThreads, smem, st>>>(a);
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int spc_cloud_fraction(spc_handle h, const uint32_t* mask, const int32_t* slab_idx, int vol_dtype, int layout, int nx,
+                       int ny, int nk, int ncol, int nlev, int out_dtype, int32_t* cntslab, void* A, void* stream) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  SPC_REQUIRE(ncol >= 0 && nlev >= 1 && nk >= 1 && nx > 0 && ny > 0, SPC_ERR_ARG, "spc_cloud_fraction: bad shape");
+  SPC_REQUIRE(out_dtype == SPC_F32 || out_dtype == SPC_F64, SPC_ERR_ARG, "spc_cloud_fraction: bad out_dtype %d", out_dtype);
+  if (ncol == 0) return SPC_OK;
+  SPC_REQUIRE(mask && slab_idx && (cntslab || A), SPC_ERR_ARG, "spc_cloud_fraction: NULL pointer");
+  const size_t per_col = spc_mask_words_per_column(vol_dtype, layout, nx, ny, nk);
+  SPC_REQUIRE(per_col > 0, SPC_ERR_UNSUPPORTED, "spc_cloud_fraction: no cloud mask format for this layout/shape");
+  const size_t smem = (size_t)nlev * sizeof(int);
+  SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_cloud_fraction: nlev=%d too large", nlev);
+  spc::DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int mw = (int)(per_col / nk);
+  const double npts = (double)nx * (double)ny;
+  if (out_dtype == SPC_F32)
+    cloud_fraction_kernel<float><<<ncol, kThreads, smem, st>>>(mask, slab_idx, mw, nk, nlev, npts, cntslab, (float*)A);
+  else
+    cloud_fraction_kernel<double><<<ncol, kThreads, smem, st>>>(mask, slab_idx, mw, nk, nlev, npts, cntslab, (double*)A);
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
 }

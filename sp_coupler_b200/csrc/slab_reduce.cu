@@ -381,7 +381,6 @@ int spc_slab_reduce(spc_handle h, const void* const vol[5], int dtype, int layou
                     double ql_thresh, double* prof, int32_t* cnt, uint32_t* mask, void* stream) {
   int rc = spc::check_handle(h);
   if (rc) return rc;
-  SPC_REQUIRE(vol && prof, SPC_ERR_ARG, "spc_slab_reduce: vol/prof is NULL");
   SPC_REQUIRE(dtype == SPC_F32 || dtype == SPC_F64, SPC_ERR_ARG, "spc_slab_reduce: bad dtype %d", dtype);
   SPC_REQUIRE(layout == SPC_LAYOUT_KJI || layout == SPC_LAYOUT_IJK, SPC_ERR_ARG, "spc_slab_reduce: bad layout %d", layout);
   SPC_REQUIRE(ncol >= 0 && nx > 0 && ny > 0 && nk > 0, SPC_ERR_ARG, "spc_slab_reduce: bad shape ncol=%d nx=%d ny=%d nk=%d",
@@ -389,6 +388,7 @@ int spc_slab_reduce(spc_handle h, const void* const vol[5], int dtype, int layou
   const long long S = (long long)nx * ny;
   SPC_REQUIRE(S * (dtype == SPC_F32 ? 4 : 8) < (1ll << 31), SPC_ERR_UNSUPPORTED, "spc_slab_reduce: slab too large");
   if (ncol == 0) return SPC_OK;
+  SPC_REQUIRE(vol && prof, SPC_ERR_ARG, "spc_slab_reduce: vol/prof is NULL");
   for (int f = 0; f < SPC_NFIELDS; ++f) SPC_REQUIRE(vol[f] != nullptr, SPC_ERR_ARG, "spc_slab_reduce: vol[%d] is NULL", f);
   SPC_REQUIRE(!(layout == SPC_LAYOUT_IJK && mask), SPC_ERR_UNSUPPORTED,
               "spc_slab_reduce: the cloud mask is only produced for the KJI layout");

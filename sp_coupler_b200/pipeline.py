@@ -1,0 +1,139 @@
+"""Device-resident batched coupling step for the columns one rank owns.
+
+This is what the `splib.step`-shaped driver (sp_coupler_b200/splib.py) and bench.py run per GCM
+time step instead of the reference's two serial Python loops over LES models
+(splib/splib.py:317-323 and :330-332):
+
+    H2D  GCM profiles of the step (one packed copy from pinned host memory)   <- gather_gcm_data
+    K2   gcm_to_les   forcings on the LES from the previous slab means        <- set_les_forcings
+         [ the LES models time-step here; external to the coupling path ]
+    K1   slab_reduce  slab means + cloud mask of the LES volumes              <- get_les_profiles
+    K3   les_to_gcm   tendencies on the GCM, packed [ncol][7][nlev]           <- set_gcm_tendencies
+    NCCL all_gather of the packed tendency block when columns are sharded
+    D2H  tendencies to the rank that owns the GCM
+
+Columns are independent, so ranks own contiguous column blocks and the only exchange is the
+tendency gather.
+"""
+import numpy as np
+import torch
+
+from .constants import surf_vars
+from .coupler import GCM_FULL, GCM_HALF
+
+
+def shard_columns(ncol_total, world_size, rank):
+    """Contiguous block partition: rank r owns [lo, hi). Remainder columns go to the first ranks."""
+    base, rem = divmod(ncol_total, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GcmStaging(object):
+    """Packed struct-of-arrays staging of the GCM inputs (gcm_vars + surf_vars, spcpl.py:32-33):
+    one pinned host buffer, one device buffer, one async copy per step."""
+
+    def __init__(self, ncol, nlev, dtype, device, pin=True):
+        self.ncol, self.nlev, self.dtype = ncol, nlev, dtype
+        sizes = [(n, (ncol, nlev)) for n in GCM_FULL] + [(n, (ncol, nlev + 1)) for n in GCM_HALF] + \
+                [(n, (ncol,)) for n in surf_vars]
+        total = sum(int(np.prod(s)) for _, s in sizes)
+        self.host_buf = torch.empty(total, dtype=dtype, pin_memory=pin and torch.cuda.is_available())
+        self.dev_buf = torch.empty(total, dtype=dtype, device=device)
+        self.host, self.dev = {}, {}
+        off = 0
+        for n, s in sizes:
+            cnt = int(np.prod(s))
+            self.host[n] = self.host_buf[off:off + cnt].view(*s)
+            self.dev[n] = self.dev_buf[off:off + cnt].view(*s)
+            off += cnt
+        self.nbytes = total * self.host_buf.element_size()
+
+    def fill_host(self, gcm):
+        """Copy a dict of numpy / CPU-tensor arrays into the pinned buffer (what the host GCM does)."""
+        for n, h in self.host.items():
+            if n in gcm:
+                h.copy_(torch.as_tensor(np.ascontiguousarray(gcm[n])) if not isinstance(gcm[n], torch.Tensor) else gcm[n])
+
+    def upload(self):
+        self.dev_buf.copy_(self.host_buf, non_blocking=True)
+        return self.dev
+
+
+class CouplingPipeline(object):
+    """State + step of the GPU coupling path for this rank's columns."""
+
+    def __init__(self, cpl, zf, zh, ncol, nlev, dtype=torch.float32, couple_surface=True, layout="kji",
+                 ql_thresh=0.0, group=None, gather=True):
+        self.cpl = cpl
+        dev = cpl.device
+        self.zf = torch.as_tensor(np.asarray(zf, dtype=np.float64)).to(dev)
+        self.zh = torch.as_tensor(np.asarray(zh, dtype=np.float64)).to(dev)
+        self.nk = int(self.zf.shape[0])
+        self.ncol, self.nlev, self.dtype = ncol, nlev, dtype
+        self.couple_surface, self.layout, self.ql_thresh = couple_surface, layout, ql_thresh
+        self.staging = GcmStaging(ncol, nlev, dtype, dev)
+        self.gcm = self.staging.dev
+        self.vols = None            # five LES volumes (device-resident LES state)
+        self.aux = None             # LES-internal profiles: QL_ice, T, Rhobf, PS ...
+        self.slab = None            # last K1 result
+        self.tend = torch.zeros((ncol, 7, nlev), dtype=dtype, device=dev)
+        self.group = group
+        self.world = 1
+        self.rank = 0
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(group)
+            self.rank = torch.distributed.get_rank(group)
+        self.gather = gather and self.world > 1
+        self.tend_all = torch.zeros((ncol * self.world, 7, nlev), dtype=dtype, device=dev) if self.gather else self.tend
+        self.tend_host = torch.empty(self.tend_all.shape, dtype=dtype, pin_memory=True)
+        self.k1_events = None       # optional [(start, end)] CUDA events around K1 (bench roofline)
+
+    # LES side --------------------------------------------------------------------------------
+    def attach_les(self, vols, aux):
+        self.vols = list(vols)
+        self.aux = aux
+
+    def les_profiles(self):
+        """K1 (get_les_profiles, spcpl.py:747-767)."""
+        if self.k1_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.slab = self.cpl.slab_reduce(self.vols, layout=self.layout, ql_thresh=self.ql_thresh,
+                                         want_mask=(self.layout in ("kji", 0)), out=self.slab)
+        if self.k1_events is not None:
+            e1.record()
+            self.k1_events.append((e0, e1))
+        return self.slab
+
+    # one coupled step -------------------------------------------------------------------------
+    def forcings(self, dt, factor):
+        """K2 (set_les_forcings for all columns, spcpl.py:299-385)."""
+        prof = self.slab["prof"] if self.slab is not None else None
+        return self.cpl.gcm_to_les(self.gcm, self.zf, self.zh, prof, self.aux["PS"] if prof is not None else None,
+                                   dt, factor, self.couple_surface)
+
+    def tendencies(self, frc, dt, factor, conservative=False):
+        """K3 (set_gcm_tendencies for all columns, spcpl.py:388-555) + the tendency gather."""
+        res = self.cpl.les_to_gcm(self.gcm, self.zf, self.zh, self.slab, self.aux, frc["slab_idx"], dt, factor,
+                                  conservative=conservative, tend_out=self.tend)
+        if self.gather:
+            torch.distributed.all_gather_into_tensor(self.tend_all, self.tend, group=self.group)
+        return res
+
+    def step_device(self, dt=900.0, f_les=1.0, f_gcm=1.0):
+        """K2 -> K1 -> K3 (+gather) with everything already resident in HBM."""
+        frc = self.forcings(dt, f_les)
+        self.les_profiles()
+        self.tendencies(frc, dt, f_gcm)
+        return frc
+
+    def step_host(self, dt=900.0, f_les=1.0, f_gcm=1.0, owner=0):
+        """The step as the host GCM sees it: GCM profiles in pinned host memory in, tendencies in
+        pinned host memory out on the rank that owns the GCM. Synchronises before returning."""
+        self.staging.upload()
+        frc = self.step_device(dt, f_les, f_gcm)
+        if self.rank == owner:
+            self.tend_host.copy_(self.tend_all, non_blocking=True)
+        torch.cuda.current_stream(self.cpl.device).synchronize()
+        return frc, self.tend_host

@@ -1,0 +1,57 @@
+"""Quick K1 bandwidth probe (not the bench): times spc_slab_reduce alone with CUDA events."""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from sp_coupler_b200 import synth
+from sp_coupler_b200.coupler import Coupler
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--ncol", type=int, default=512)
+ap.add_argument("--nx", type=int, default=64)
+ap.add_argument("--nk", type=int, default=160)
+ap.add_argument("--dtype", default="f32")
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--layout", default="kji")
+ap.add_argument("--nomask", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+cpl = Coupler(dev)
+td = torch.float32 if a.dtype == "f32" else torch.float64
+zf, zh = synth.les_grid(a.nk)
+gcm = synth.make_gcm_columns(a.ncol, 91)
+t0 = time.time()
+vols = synth.device_les_volumes(cpl, gcm, zf, a.nx, a.nx, dtype=td)
+torch.cuda.synchronize()
+print("generated %.2f GB in %.2fs" % (sum(v.numel() * v.element_size() for v in vols) / 1e9, time.time() - t0))
+if a.layout == "ijk":
+    vols = [v.permute(0, 3, 2, 1).contiguous() for v in vols]
+nbytes = sum(v.numel() * v.element_size() for v in vols)
+for _ in range(3):
+    s = cpl.slab_reduce(vols, layout=a.layout, want_mask=not a.nomask and a.layout == "kji")
+torch.cuda.synchronize()
+ts = []
+for _ in range(a.iters):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s = cpl.slab_reduce(vols, layout=a.layout, want_mask=not a.nomask and a.layout == "kji")
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+ts = np.array(ts)
+print("K1 %s ncol=%d %dx%dx%d %s: median %.3f ms min %.3f ms -> %.1f GB/s (median) %.1f GB/s (best); %.0f col/s"
+      % (a.layout, a.ncol, a.nx, a.nx, a.nk, a.dtype, np.median(ts), ts.min(), nbytes / np.median(ts) / 1e6,
+         nbytes / ts.min() / 1e6, a.ncol / np.median(ts) * 1e3))
+# set_les_state write bandwidth
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+prof = torch.zeros((a.ncol, a.nk), dtype=torch.float64, device=dev)
+e0.record()
+cpl.set_les_state(prof, 0.1, 0, a.nx, a.nx, dtype=td, out=vols[0] if a.layout == "kji" else None)
+e1.record()
+torch.cuda.synchronize()
+print("set_les_state: %.3f ms -> %.1f GB/s written" % (e0.elapsed_time(e1), vols[0].numel() * vols[0].element_size() / e0.elapsed_time(e1) / 1e6))
