@@ -1,0 +1,137 @@
+"""The host-side mirror of the reference interface (sp_coupler_b200/{spcpl,sputils,splib,spdummy}.py):
+per-LES reference-shaped calls and the batched route must give the same numbers as the oracle."""
+import numpy as np
+import pytest
+
+import cases
+from conftest import relerr
+from oracle import numpy_batched as nb
+from sp_coupler_b200.constants import LES_FIELDS, TENDENCIES, gcm_vars, surf_vars
+
+pytestmark = pytest.mark.gpu
+
+
+def n(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture()
+def world(cuda_device):
+    """A 6-column GPU stand-in world driven through splib.initialize."""
+    from sp_coupler_b200 import splib
+    splib.initialize(dict(max_num_les=6, les_nx=16, les_ny=16, les_nk=160, gcm_nlev=91, dtype="f64",
+                          cplsurf=True, per_column=False, write_diagnostics=False), device=cuda_device)
+    return splib
+
+
+def host_world(splib):
+    b = splib.les_batch
+    gcm = {k: splib.gcm_model.state[k][:b.ncol] for k in gcm_vars + surf_vars}
+    vols = {f: n(v) for f, v in zip(LES_FIELDS, b.vols)}
+    aux = {k: n(v) for k, v in b.aux.items()}
+    return gcm, vols, aux
+
+
+def test_batched_step_matches_oracle(world, cuda_device):
+    splib = world
+    b = splib.les_batch
+    gcm, vols, aux = host_world(splib)
+    ref = nb.coupling_step(gcm, b.zf_host, b.zh_host, vols, aux, aux["PS"], 900.0, 1.0, 1.0, True)
+    from sp_coupler_b200 import spcpl
+    spcpl.gather_gcm_data(splib.gcm_model, splib.les_models, True)
+    frc = spcpl.set_les_forcings_all(b, 900.0, 1.0, True, firststep=True)
+    spcpl.get_les_profiles_all(b)
+    res = spcpl.set_gcm_tendencies_all(splib.gcm_model, b, 900.0, 1.0)
+    for k in ("f_u", "f_v", "f_thl", "f_qt", "f_ql", "f_ps", "wthl", "wqt"):
+        assert relerr(n(frc[k]), ref["forcings"][k]) <= 1e-6, k
+    for k in TENDENCIES:
+        assert relerr(n(res[k]), ref["tendencies"][k]) <= 1e-6, k
+    # the GCM received the packed block
+    idx, arr = splib.gcm_model.tendencies["T"]["batch"]
+    assert relerr(arr, ref["tendencies"]["f_T"]) <= 1e-6
+
+
+def test_per_column_calls_match_batched_and_oracle(world, cuda_device):
+    splib = world
+    from sp_coupler_b200 import spcpl, sputils
+    b = splib.les_batch
+    gcm, vols, aux = host_world(splib)
+    ref = nb.coupling_step(gcm, b.zf_host, b.zh_host, vols, aux, aux["PS"], 900.0, 0.5, 2.0, True)
+    spcpl.gather_gcm_data(splib.gcm_model, splib.les_models, True)
+    for les in splib.les_models[:3]:
+        i = les.i
+        req = spcpl.set_les_forcings(les, splib.gcm_model, True, True, {}, 900.0, 0.5, True, write=False)
+        assert set(req) == {"U", "V", "THL", "QT", "SP", "QL", "QLp", "Z0M_surf", "Z0H_surf", "WT_surf", "WQ_surf"}
+        assert all(hasattr(r, "result") for r in req.values())
+        assert relerr(n(b.tend["THL"][i]), ref["forcings"]["f_thl"][i]) <= 1e-6
+        assert relerr(n(b.tend["U"][i]), ref["forcings"]["f_u"][i]) <= 1e-6
+        assert relerr(n(b.ql_ref[i]), ref["forcings"]["ql_ref"][i]) <= 1e-6
+        assert relerr(n(les.gcm_Zf), ref["forcings"]["Zf"][i]) == 0.0
+        prof = {k: v.result() for k, v in spcpl.get_les_profiles(les, True).items()}
+        assert set(prof) == {"U", "V", "presf", "Rhof", "Rhobf", "THL", "QT", "QL", "QL_ice", "QR", "PS", "T", "A", "Rain"}
+        assert relerr(n(prof["A"]), ref["cntslab"][i] / 256.0) <= 1e-12
+        assert relerr(n(prof["THL"]), ref["prof"]["THL"][i]) <= 1e-12
+        # spcpl.get_cloud_fraction: same numbers, reversed to GCM order (spcpl.py:28)
+        assert relerr(n(spcpl.get_cloud_fraction(les)), (ref["cntslab"][i] / 256.0)[::-1]) <= 1e-12
+        spcpl.set_gcm_tendencies(splib.gcm_model, les, prof, 900.0, factor=2.0, write=False)
+        for name, key in (("T", "f_T"), ("SH", "f_SH"), ("QL", "f_QL"), ("QI", "f_QI"), ("U", "f_U"), ("V", "f_V"), ("A", "f_A")):
+            assert relerr(splib.gcm_model.tendencies[name][les.grid_index], ref["tendencies"][key][i]) <= 1e-6, name
+        u, v, thl, qt, ps, ql = spcpl.convert_profiles(les, write=False)
+        assert relerr(n(thl), ref["forcings"]["thl"][i]) <= 1e-12
+        assert relerr(n(ps), ref["forcings"]["ps"][i]) == 0.0
+        z0m, z0h, wthl, wqt = spcpl.convert_surface_fluxes(les)
+        assert relerr(n(wthl), ref["forcings"]["wthl"][i]) <= 1e-12
+    # sputils mirror
+    p = b.pipe.gcm["Pfull"][0]
+    assert relerr(n(sputils.exner(p) * sputils.iexner(p)), np.ones(91)) <= 1e-14
+    x = b.pipe.zf
+    Zf = splib.les_models[0].gcm_Zf.flip(0).contiguous()
+    out = sputils.interp(x, Zf, b.pipe.gcm["U"][0].flip(0).contiguous())
+    assert np.array_equal(n(out), np.interp(b.zf_host, n(Zf), n(b.pipe.gcm["U"][0])[::-1]))
+    assert int(sputils.searchsorted(-splib.les_models[0].gcm_Zf, -x[-1])) == int(ref["tendencies"]["start_index"][0])
+
+
+def test_driver_loop_runs_and_both_routes_agree(cuda_device):
+    """splib.initialize/run/finalize with per-LES calls vs the batched route: identical GCM state."""
+    from sp_coupler_b200 import splib
+    cfg = dict(max_num_les=4, les_nx=16, les_ny=16, les_nk=160, gcm_nlev=19, dtype="f64", cplsurf=True,
+               write_diagnostics=False)
+    states = []
+    for per_column in (False, True):
+        splib.initialize(dict(cfg, per_column=per_column), device=cuda_device)
+        splib.run(3)
+        splib.finalize()
+        assert len(splib.timing_rows) == 3 and splib.gcm_model.model_time == 3 * 900.0
+        states.append({k: splib.gcm_model.state[k][:4].copy() for k in ("T", "SH", "U", "A")})
+    for k in states[0]:
+        assert relerr(states[1][k], states[0][k]) <= 1e-12, k
+    # the coupling did something: relaxation pulled the LES means toward the GCM
+    assert np.isfinite(states[0]["T"]).all()
+
+
+def test_set_les_state_and_diagnostics_store(world, cuda_device):
+    import torch
+    from sp_coupler_b200 import spcpl, spio, synth
+    splib = world
+    les = splib.les_models[2]
+    spcpl.gather_gcm_data(splib.gcm_model, splib.les_models, True)
+    u, v, thl, qt, ps, ql = spcpl.convert_profiles(les, write=False)
+    spcpl.set_les_state(les, u, v, thl, qt, ps)
+    b = splib.les_batch
+    vol = n(b.vols[LES_FIELDS.index("THL")][les.i])
+    host = synth.les_state_volume(n(thl)[None, :], 0.1, synth.STREAM["THL"], b.nx, b.ny, seed=b.seed, col0=les.i,
+                                  dtype=np.float64)[0]
+    assert np.array_equal(vol, host)
+    assert abs(vol.mean(axis=(1, 2)) - n(thl)).max() < 0.1 * 4 / np.sqrt(256)      # uniform noise, amplitude 0.1 K
+    # diagnostics keep the reference's spifs.nc variable names
+    spio.init_netcdf("unused.npz", splib.gcm_model, splib.les_models)
+    spio.update_time(0.0)
+    spcpl.set_les_forcings(les, splib.gcm_model, False, True, {}, 900.0, 1.0, True, write=True)
+    prof = spcpl.get_les_profiles(les, False)
+    spcpl.set_gcm_tendencies(splib.gcm_model, les, prof, 900.0, write=True)
+    names = set(les.cdf)
+    for want in ("U", "V", "T", "SH", "QL", "QI", "Pf", "Ph", "Zf", "Zh", "Psurf", "Tv", "THL", "QT", "f_u", "f_v", "f_thl",
+                 "f_qt", "rain", "rainrate", "z0m", "z0h", "wthl", "wqt", "TLflux", "TSflux", "SHflux", "QLflux", "QIflux",
+                 "u", "v", "presf", "rhof", "rhobf", "qt", "ql", "ql_ice", "ql_water", "thl", "t", "t_", "qr",
+                 "f_U", "f_V", "f_T", "f_SH", "A", "A_d", "f_QL", "f_QI", "f_A"):
+        assert want in names, want
