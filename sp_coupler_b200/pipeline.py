@@ -29,6 +29,15 @@ def shard_columns(ncol_total, world_size, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def gather_tendencies(tend_local, tend_all, group=None):
+    """The path's only exchange: all_gather of the packed [ncol_local][7][nlev]
+    tendency blocks into [ncol_local*world][7][nlev] so the rank that owns the GCM holds every
+    column's tendencies (reference analogue: 7 set_profile_tendency RPCs per column,
+    spcpl.py:535-542). NCCL on device tensors, gloo on CPU tensors (tests)."""
+    torch.distributed.all_gather_into_tensor(tend_all, tend_local, group=group)
+    return tend_all
+
+
 class GcmStaging(object):
     """Packed struct-of-arrays staging of the GCM inputs (gcm_vars + surf_vars, spcpl.py:32-33):
     one pinned host buffer, one device buffer, one async copy per step."""
@@ -118,7 +127,7 @@ class CouplingPipeline(object):
         res = self.cpl.les_to_gcm(self.gcm, self.zf, self.zh, self.slab, self.aux, frc["slab_idx"], dt, factor,
                                   conservative=conservative, tend_out=self.tend)
         if self.gather:
-            torch.distributed.all_gather_into_tensor(self.tend_all, self.tend, group=self.group)
+            gather_tendencies(self.tend, self.tend_all, self.group)
         return res
 
     def step_device(self, dt=900.0, f_les=1.0, f_gcm=1.0):
