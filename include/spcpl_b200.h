@@ -128,6 +128,8 @@ typedef struct {
   const void* A;           /* optional [ncol][nlev] cloud fraction, ascending slab order, dtype */
   const uint32_t* mask;    /* else: cloud mask from spc_slab_reduce + slab_idx below            */
   const int32_t* slab_idx; /* [ncol][nlev] from spc_gcm_to_les                                 */
+  const int32_t* cnt;      /* optional [ncol][nk] counts from spc_slab_reduce: lets cloud-free
+                              levels be skipped without reading their mask words               */
   int vol_dtype, layout, nx, ny; /* describe the volumes `mask` was built from                 */
 } spc_les_prof;
 
@@ -149,8 +151,9 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
  * GCM slab from the spc_slab_reduce mask. slab_idx [ncol][nlev] ascending (spc_gcm_to_les);
  * cntslab int32 [ncol][nlev] and/or A = cntslab/(nx*ny) of out_dtype, both in ascending slab order
  * (the order get_cloudfraction returns; the coupler reverses it, spcpl.py:28,404). */
-int spc_cloud_fraction(spc_handle h, const uint32_t* mask, const int32_t* slab_idx, int vol_dtype, int layout,
-                       int nx, int ny, int nk, int ncol, int nlev, int out_dtype,
+int spc_cloud_fraction(spc_handle h, const uint32_t* mask, const int32_t* slab_idx,
+                       const int32_t* cnt /* optional [ncol][nk], as in spc_les_prof */,
+                       int vol_dtype, int layout, int nx, int ny, int nk, int ncol, int nlev, int out_dtype,
                        int32_t* cntslab, void* A, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

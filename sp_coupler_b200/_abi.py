@@ -36,7 +36,7 @@ class LesForcing(C.Structure):
 
 class LesProf(C.Structure):
     """struct spc_les_prof"""
-    _fields_ = [(n, _vp) for n in ("prof", "QL_ice", "T", "Rhobf", "A", "mask", "slab_idx")] + \
+    _fields_ = [(n, _vp) for n in ("prof", "QL_ice", "T", "Rhobf", "A", "mask", "slab_idx", "cnt")] + \
                [(n, _i) for n in ("vol_dtype", "layout", "nx", "ny")]
 
 
@@ -69,7 +69,7 @@ def lib():
                                  C.POINTER(LesForcing), _vp]
     L.spc_les_to_gcm.argtypes = [_vp, C.POINTER(GcmCols), _vp, _vp, _i, C.POINTER(LesProf), _d, _d, _i,
                                  C.POINTER(GcmTend), _vp]
-    L.spc_cloud_fraction.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]
+    L.spc_cloud_fraction.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]
     L.spc_interp.argtypes = [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]
     L.spc_searchsorted.argtypes = [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]
     L.spc_exner.argtypes = [_vp, _i, _vp, C.c_size_t, _i, _vp, _vp]

@@ -200,6 +200,8 @@ class Coupler(object):
                 raise ValueError("slab_idx (from gcm_to_les) is needed to project the cloud mask")
             lp.mask = slab["mask"].data_ptr()
             lp.slab_idx = self._chk(slab_idx, "slab_idx", torch.int32, (ncol, nlev)).data_ptr()
+            if slab.get("cnt") is not None:
+                lp.cnt = slab["cnt"].data_ptr()
             lp.vol_dtype, lp.layout, lp.nx, lp.ny = _DT[slab["dtype"]], slab["layout"], slab["nx"], slab["ny"]
         o = _abi.GcmTend()
         tend = tend_out if tend_out is not None else self._empty((ncol, 7, nlev), dtype)
@@ -239,7 +241,8 @@ class Coupler(object):
             raise ValueError("slab_reduce was run without want_mask")
         A = self._empty((ncol, nlev), dtype)
         cs = self._empty((ncol, nlev), torch.int32)
-        _abi.check(self._lib.spc_cloud_fraction(self._h, _ptr(slab["mask"]), _ptr(slab_idx), _DT[slab["dtype"]],
+        _abi.check(self._lib.spc_cloud_fraction(self._h, _ptr(slab["mask"]), _ptr(slab_idx), _ptr(slab.get("cnt")),
+                                                _DT[slab["dtype"]],
                                                 slab["layout"], slab["nx"], slab["ny"], nk, ncol, nlev, _DT[dtype],
                                                 _ptr(cs), _ptr(A), self._stream()), "spc_cloud_fraction")
         self.launches += 1

@@ -170,30 +170,55 @@ __device__ double integral_w(double a, double b, const double* z, int n, const d
 // [idx[r-1], idx[r]) (idx[-1] := 0, clipped to nk); cslab[r] += number of horizontal points with
 // any cloudy cell in the slab (les.get_cloudfraction(indices), spcpl.py:28,765). The mask layout
 // is opaque but identical for every level, so OR over k then popcount is layout-independent.
-// cslab must be zeroed by the caller; integer atomics in shared memory keep the result exact.
-__device__ __forceinline__ void project_cloud_mask(const uint32_t* m, const int32_t* idx, int mw, int nk, int nlev,
-                                                   int* cslab) {
-  for (int w = threadIdx.x; w < mw; w += blockDim.x) {
-    int k0 = 0;
-    for (int r = 0; r < nlev && k0 < nk; ++r) {
-      const int k1 = min(max(__ldg(idx + r), k0), nk);
-      uint32_t acc = 0;
-      for (int k = k0; k < k1; ++k) acc |= __ldg(m + (size_t)k * mw + w);
-      if (acc) atomicAdd(&cslab[r], __popc(acc));
-      k0 = k1;
+// `cnt` (optional, the per-level counts of K1) lets cloud-free levels be skipped without touching
+// their mask words. cslab must be zeroed by the caller; results are exact integers.
+__device__ __forceinline__ void project_cloud_mask(const uint32_t* m, const int32_t* idx, const int32_t* cnt, int mw,
+                                                   int nk, int nlev, int* cslab) {
+  constexpr int B = 8;  // levels fetched per batch: 8 independent loads in flight per thread
+  const int mw_pad = (mw + 31) & ~31;  // warp-uniform trip count so that the warp reductions are full
+  for (int w = threadIdx.x; w < mw_pad; w += blockDim.x) {
+    const bool valid = w < mw;
+    int r = 0;
+    int kend = min(max(__ldg(idx), 0), nk);  // exclusive end of slab r (monotone, clipped)
+    uint32_t acc = 0;
+    for (int kb = 0; kb < nk && r < nlev; kb += B) {
+      uint32_t v[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        const int k = kb + i;
+        const bool live = valid && k < nk && (cnt == nullptr || __ldg(cnt + k) != 0);
+        v[i] = live ? __ldg(m + (size_t)k * mw + w) : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        const int k = kb + i;
+        while (r < nlev && k >= kend) {  // close slab r (possibly empty), open the next one
+          const int n = __reduce_add_sync(0xffffffffu, __popc(acc));
+          if (n && (threadIdx.x & 31) == 0) atomicAdd(&cslab[r], n);
+          acc = 0;
+          if (++r < nlev) kend = min(max(__ldg(idx + r), kend), nk);
+        }
+        if (r < nlev) acc |= v[i];
+      }
+    }
+    if (r < nlev) {  // slab that runs to the LES top
+      const int n = __reduce_add_sync(0xffffffffu, __popc(acc));
+      if (n && (threadIdx.x & 31) == 0) atomicAdd(&cslab[r], n);
     }
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads) cloud_fraction_kernel(const uint32_t* mask, const int32_t* slab_idx, int mw,
-                                                                  int nk, int nlev, double npts, int32_t* cntslab, T* A) {
+__global__ void __launch_bounds__(kThreads) cloud_fraction_kernel(const uint32_t* mask, const int32_t* slab_idx,
+                                                                  const int32_t* cnt, int mw, int nk, int nlev,
+                                                                  double npts, int32_t* cntslab, T* A) {
   extern __shared__ __align__(16) double sm[];
   int* cslab = reinterpret_cast<int*>(sm);
   const int c = blockIdx.x;
   for (int l = threadIdx.x; l < nlev; l += kThreads) cslab[l] = 0;
   __syncthreads();
-  project_cloud_mask(mask + (size_t)c * nk * mw, slab_idx + (size_t)c * nlev, mw, nk, nlev, cslab);
+  project_cloud_mask(mask + (size_t)c * nk * mw, slab_idx + (size_t)c * nlev, cnt ? cnt + (size_t)c * nk : nullptr, mw, nk,
+                     nlev, cslab);
   __syncthreads();
   for (int l = threadIdx.x; l < nlev; l += kThreads) {
     if (cntslab) cntslab[(size_t)c * nlev + l] = cslab[l];
@@ -265,7 +290,9 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
 
   // projected cloud cover per GCM slab from the K1 bit mask
   const bool from_mask = (a.les.A == nullptr) && a.les.mask && a.les.slab_idx;
-  if (from_mask) project_cloud_mask(a.les.mask + (size_t)c * nk * a.mask_words, a.les.slab_idx + b, a.mask_words, nk, nlev, cslab);
+  if (from_mask)
+    project_cloud_mask(a.les.mask + (size_t)c * nk * a.mask_words, a.les.slab_idx + b,
+                       a.les.cnt ? a.les.cnt + (size_t)c * nk : nullptr, a.mask_words, nk, nlev, cslab);
   if (threadIdx.x == 0) {
     // start_index = searchsorted(-Zf, -h[-1]) (spcpl.py:498): GCM levels strictly above the LES top.
     // -Zf ascending <=> ZfA descending index; count of Zf > h_top = nlev - upper_bound(ZfA, h_top)
@@ -449,8 +476,9 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   return SPC_OK;
 }
 
-int spc_cloud_fraction(spc_handle h, const uint32_t* mask, const int32_t* slab_idx, int vol_dtype, int layout, int nx,
-                       int ny, int nk, int ncol, int nlev, int out_dtype, int32_t* cntslab, void* A, void* stream) {
+int spc_cloud_fraction(spc_handle h, const uint32_t* mask, const int32_t* slab_idx, const int32_t* cnt, int vol_dtype,
+                       int layout, int nx, int ny, int nk, int ncol, int nlev, int out_dtype, int32_t* cntslab, void* A,
+                       void* stream) {
   int rc = spc::check_handle(h);
   if (rc) return rc;
   SPC_REQUIRE(ncol >= 0 && nlev >= 1 && nk >= 1 && nx > 0 && ny > 0, SPC_ERR_ARG, "spc_cloud_fraction: bad shape");
@@ -466,9 +494,9 @@ int spc_cloud_fraction(spc_handle h, const uint32_t* mask, const int32_t* slab_i
   const int mw = (int)(per_col / nk);
   const double npts = (double)nx * (double)ny;
   if (out_dtype == SPC_F32)
-    cloud_fraction_kernel<float><<<ncol, kThreads, smem, st>>>(mask, slab_idx, mw, nk, nlev, npts, cntslab, (float*)A);
+    cloud_fraction_kernel<float><<<ncol, kThreads, smem, st>>>(mask, slab_idx, cnt, mw, nk, nlev, npts, cntslab, (float*)A);
   else
-    cloud_fraction_kernel<double><<<ncol, kThreads, smem, st>>>(mask, slab_idx, mw, nk, nlev, npts, cntslab, (double*)A);
+    cloud_fraction_kernel<double><<<ncol, kThreads, smem, st>>>(mask, slab_idx, cnt, mw, nk, nlev, npts, cntslab, (double*)A);
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
 }

@@ -5,18 +5,27 @@
 // byte is read exactly once; algorithmic bytes = 5*nx*ny*nk*sizeof(T) per column.
 //
 // Fast path (KJI layout, slab bytes % 16 == 0): persistent grid, one CTA per SM, every WARP owns a
-// private ring of NST shared-memory stages fed by 1-D TMA bulk copies (cp.async.bulk +
-// mbarrier complete_tx). Lane 0 keeps NST chunks in flight; the warp reduces a landed chunk with
+// private ring of shared-memory stages fed by 1-D TMA bulk copies (cp.async.bulk + mbarrier
+// complete_tx). Lane 0 keeps the ring full; the warp reduces a landed chunk in 4 KB sub-blocks with
 // conflict-free 128-bit LDS, accumulating in float64 (so the mean is order-insensitive to ~1e-16),
 // and finishes a slab with a shuffle butterfly. No block-wide barriers, no atomics, fixed order.
 #include "spc_common.cuh"
 
 namespace {
 
-constexpr int kWarps = 16;      // warps per CTA (one CTA per SM)
-constexpr int kChunk = 4096;    // bytes per TMA bulk copy / ring stage
-constexpr int kStages = 3;      // ring depth per warp -> 16*3*4 KB = 192 KB in flight per SM
+// Shape of the per-warp TMA ring: WARPS warps per CTA (one CTA per SM), STAGES stages of CHUNK bytes
+// each (CHUNK = NSUB x 4 KB sub-blocks; a sub-block is what one warp reduces per pass and one cloud-mask
+// word per lane). BLOCKED: a warp owns a contiguous run of slabs instead of every nwarps-th slab.
+template <int WARPS_, int CHUNK_, int STAGES_, bool BLOCKED_ = false>
+struct Ring {
+  static constexpr int kWarps = WARPS_, kChunk = CHUNK_, kStages = STAGES_;
+  static constexpr bool kBlocked = BLOCKED_;
+  static_assert(CHUNK_ % 4096 == 0, "chunk must be a multiple of the 4 KB sub-block");
+  static_assert((size_t)WARPS_ * STAGES_ * (CHUNK_ + 8) <= 227 * 1024, "ring exceeds shared memory");
+};
+constexpr int kSubBytes = 4096;
 constexpr uint32_t kFull = 0xffffffffu;
+int g_k1_variant = 0;  // tuning hook (spc_tune_k1); 0 = production default
 
 struct K1Args {
   const void *v0, *v1, *v2, *v3, *v4;  // THL,QT,QL,U,V (named members: no local-memory copy for vol[f])
@@ -28,7 +37,8 @@ struct K1Args {
   long long total;      // 5*ncol*nk
   int S;                // elements per slab
   int slab_bytes;
-  int nch;              // chunks per slab
+  int nch;              // TMA chunks per slab
+  int nsub;             // 4 KB sub-blocks per slab (= cloud-mask words per lane per slab)
 };
 
 __device__ __forceinline__ const void* field_ptr(const K1Args& a, int f) {
@@ -78,15 +88,17 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
-// One lane's share of a landed chunk: 16-byte vectors lane, lane+32, ... of `nvec`.
+// One lane's share of a landed 4 KB sub-block: 16-byte vectors lane, lane+32, ... of `nvec` (<= 256).
+// Returns the lane's cloud bits (ql only): bit it*4+c (float32) / it*2+c (float64).
 template <typename T, bool QL>
-__device__ __forceinline__ void consume(const uint8_t* buf, int nvec, int lane, double (&acc)[4], int& cnt,
-                                        uint32_t& bits, double thr) {
-  constexpr int kIter = kChunk / 16 / 32;  // 8
+__device__ __forceinline__ uint32_t consume(const uint8_t* buf, int nvec, int lane, double (&acc)[4], int& cnt, double thr) {
+  constexpr int kIter = kSubBytes / 16 / 32;  // 8
+  constexpr int kFullVec = kSubBytes / 16;    // 256
+  uint32_t bits = 0;
   if constexpr (sizeof(T) == 4) {
     const float4* b = reinterpret_cast<const float4*>(buf);
     float4 v[kIter];
-    if (nvec == kChunk / 16) {
+    if (nvec == kFullVec) {
 #pragma unroll
       for (int it = 0; it < kIter; ++it) v[it] = b[it * 32 + lane];
     } else {
@@ -103,7 +115,7 @@ __device__ __forceinline__ void consume(const uint8_t* buf, int nvec, int lane, 
       acc[3] += d3;
       if constexpr (QL) {
         // padding lanes hold 0.0 and must not count when thr < 0
-        bool in = (nvec == kChunk / 16) || (it * 32 + lane < nvec);
+        bool in = (nvec == kFullVec) || (it * 32 + lane < nvec);
         uint32_t m = (uint32_t)(in && d0 > thr) | ((uint32_t)(in && d1 > thr) << 1) |
                      ((uint32_t)(in && d2 > thr) << 2) | ((uint32_t)(in && d3 > thr) << 3);
         cnt += __popc(m);
@@ -113,7 +125,7 @@ __device__ __forceinline__ void consume(const uint8_t* buf, int nvec, int lane, 
   } else {
     const double2* b = reinterpret_cast<const double2*>(buf);
     double2 v[kIter];
-    if (nvec == kChunk / 16) {
+    if (nvec == kFullVec) {
 #pragma unroll
       for (int it = 0; it < kIter; ++it) v[it] = b[it * 32 + lane];
     } else {
@@ -125,17 +137,19 @@ __device__ __forceinline__ void consume(const uint8_t* buf, int nvec, int lane, 
       acc[(2 * it) & 3] += v[it].x;
       acc[(2 * it + 1) & 3] += v[it].y;
       if constexpr (QL) {
-        bool in = (nvec == kChunk / 16) || (it * 32 + lane < nvec);
+        bool in = (nvec == kFullVec) || (it * 32 + lane < nvec);
         uint32_t m = (uint32_t)(in && v[it].x > thr) | ((uint32_t)(in && v[it].y > thr) << 1);
         cnt += __popc(m);
         bits |= m << (it * 2);
       }
     }
   }
+  return bits;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kWarps * 32, 1) slab_reduce_tma_kernel(const K1Args a) {
+template <typename T, typename R>
+__global__ void __launch_bounds__(R::kWarps * 32, 1) slab_reduce_tma_kernel(const K1Args a) {
+  constexpr int kWarps = R::kWarps, kChunk = R::kChunk, kStages = R::kStages;
   extern __shared__ __align__(128) uint8_t smem[];
   // [kWarps][kStages][kChunk] data, then [kWarps][kStages] mbarriers
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarps * kStages * kChunk);
@@ -152,18 +166,29 @@ __global__ void __launch_bounds__(kWarps * 32, 1) slab_reduce_tma_kernel(const K
   }
   __syncwarp();
 
+  // slabs of this warp: g(i) = g0 + i*gstride, i < nslab
   const long long nwarps = (long long)gridDim.x * kWarps;
   const long long gw = (long long)blockIdx.x * kWarps + warp;
-  if (gw >= a.total) return;
-  const long long nslab = (a.total - gw + nwarps - 1) / nwarps;  // slabs gw, gw+nwarps, ...
-  const long long nq = nslab * a.nch;                              // chunks this warp streams
+  long long g0, gstride, nslab;
+  if constexpr (R::kBlocked) {
+    const long long base = a.total / nwarps, rem = a.total % nwarps;
+    g0 = gw * base + min(gw, rem);
+    nslab = base + (gw < rem ? 1 : 0);
+    gstride = 1;
+  } else {
+    g0 = gw;
+    gstride = nwarps;
+    nslab = gw < a.total ? (a.total - gw + nwarps - 1) / nwarps : 0;
+  }
+  if (nslab == 0) return;
+  const long long nq = nslab * a.nch;  // chunks this warp streams
   const uint64_t pol = l2_evict_first_policy();
 
   // producer state (lane 0): next chunk to issue
   long long pi = 0;  // slab ordinal
   int pj = 0;        // chunk within slab
   auto issue = [&](int stage) {
-    const long long g = gw + pi * nwarps;
+    const long long g = g0 + pi * gstride;
     const int f = (int)(g / a.per_field);
     const long long rem = g - (long long)f * a.per_field;
     const uint8_t* src = static_cast<const uint8_t*>(field_ptr(a, f)) + (size_t)rem * a.slab_bytes + (size_t)pj * kChunk;
@@ -185,24 +210,29 @@ __global__ void __launch_bounds__(kWarps * 32, 1) slab_reduce_tma_kernel(const K
   uint32_t parity = 0;
   long long q = 0;
   for (long long i = 0; i < nslab; ++i) {
-    const long long g = gw + i * nwarps;
+    const long long g = g0 + i * gstride;
     const int f = (int)(g / a.per_field);
     const long long rem = g - (long long)f * a.per_field;  // = c*nk + k
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     int cnt = 0;
     const bool is_ql = (f == SPC_QL) && (a.cnt != nullptr || a.mask != nullptr);
+    uint32_t* mrow = a.mask ? a.mask + (size_t)rem * a.nsub * 32 + lane : nullptr;
+    int sub_id = 0;  // 4 KB sub-block ordinal within the slab
     for (int j = 0; j < a.nch; ++j, ++q) {
       const uint32_t bar = wbar_s + 8 * stage;
       while (!mbar_try_wait(bar, parity)) {
       }
       const int bytes = min(kChunk, a.slab_bytes - j * kChunk);
       const uint8_t* buf = wbuf + stage * kChunk;
-      uint32_t bits = 0;
-      if (is_ql) {
-        consume<T, true>(buf, bytes >> 4, lane, acc, cnt, bits, a.thr);
-        if (a.mask) a.mask[((size_t)rem * a.nch + j) * 32 + lane] = bits;
-      } else {
-        consume<T, false>(buf, bytes >> 4, lane, acc, cnt, bits, a.thr);
+#pragma unroll 1
+      for (int off = 0; off < bytes; off += kSubBytes, ++sub_id) {
+        const int nvec = min(kSubBytes, bytes - off) >> 4;
+        if (is_ql) {
+          const uint32_t bits = consume<T, true>(buf + off, nvec, lane, acc, cnt, a.thr);
+          if (mrow) mrow[(size_t)sub_id * 32] = bits;
+        } else {
+          consume<T, false>(buf + off, nvec, lane, acc, cnt, a.thr);
+        }
       }
       __syncwarp();  // every lane is done reading this stage before it is refilled
       if (lane == 0 && q + kStages < nq) issue(stage);
@@ -317,18 +347,54 @@ bool fast_path(int dtype, long long S) {
   return slab_bytes % 16 == 0 && slab_bytes >= 1024;
 }
 
+template <typename T, typename R>
+int launch_tma(spc_handle h, const K1Args& a, cudaStream_t st) {
+  const size_t smem = (size_t)R::kWarps * R::kStages * R::kChunk + (size_t)R::kWarps * R::kStages * 8;
+  static thread_local int configured_dev = -1;
+  if (configured_dev != h->device) {
+    SPC_CUDA(cudaFuncSetAttribute(slab_reduce_tma_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_dev = h->device;
+  }
+  const long long want = (a.total + R::kWarps - 1) / R::kWarps;
+  const int grid = (int)std::min<long long>(h->num_sms, std::max<long long>(want, 1));
+  slab_reduce_tma_kernel<T, R><<<grid, R::kWarps * 32, smem, st>>>(a);
+  return SPC_OK;
+}
+
+// Ring shapes. Production picks by slab size (round-1 sweep on B200, profiles/README.md): about
+// 96 KB in flight per SM in single-stage per-warp rings is the sweet spot - deeper rings (192 KB)
+// cost ~8 % of bandwidth, fewer than 8 warps cannot keep up with the float32->float64 conversions.
+//   slab >= 8 KB : 12 warps x 1 x 8 KB      slab < 8 KB : 24 warps x 1 x 4 KB
+// Variants 1.. exist for tools/k1_probe.py (spc_tune_k1) and document the sweep.
+#define SPC_K1_VARIANTS(X)                                                               \
+  X(1, 12, 8192, 1, false) X(2, 24, 4096, 1, false) X(3, 16, 4096, 3, false) X(4, 8, 8192, 2, false) \
+  X(5, 8, 16384, 1, false) X(6, 16, 4096, 2, false) X(7, 12, 8192, 2, false) X(8, 12, 8192, 1, true)
+
+int k1_variant_for(int slab_bytes) {
+  if (g_k1_variant != 0) return g_k1_variant;
+  return slab_bytes >= 8192 ? 1 : 2;
+}
+
+int k1_chunk_bytes(int slab_bytes) {
+  switch (k1_variant_for(slab_bytes)) {
+#define X(id, w, c, s, b) case id: return c;
+    SPC_K1_VARIANTS(X)
+#undef X
+    default: return 4096;
+  }
+}
+
 template <typename T>
 int launch_kji(spc_handle h, const K1Args& a, bool fast, cudaStream_t st) {
   if (fast) {
-    const size_t smem = (size_t)kWarps * kStages * kChunk + (size_t)kWarps * kStages * 8;
-    static thread_local int configured_dev = -1;
-    if (configured_dev != h->device) {
-      SPC_CUDA(cudaFuncSetAttribute(slab_reduce_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured_dev = h->device;
+    int rc;
+    switch (k1_variant_for(a.slab_bytes)) {
+#define X(id, w, c, s, b) case id: rc = launch_tma<T, Ring<w, c, s, b>>(h, a, st); break;
+      SPC_K1_VARIANTS(X)
+#undef X
+      default: rc = SPC_ERR_ARG; spc::set_error("unknown K1 variant %d", g_k1_variant); break;
     }
-    const long long want = (a.total + kWarps - 1) / kWarps;
-    const int grid = (int)std::min<long long>(h->num_sms, std::max<long long>(want, 1));
-    slab_reduce_tma_kernel<T><<<grid, kWarps * 32, smem, st>>>(a);
+    if (rc) return rc;
   } else {
     const long long want = (a.total + 7) / 8;
     const int grid = (int)std::min<long long>((long long)h->num_sms * 8, std::max<long long>(want, 1));
@@ -367,12 +433,18 @@ int launch_ijk(spc_handle h, const K1Args& a, int ncol, int nk, cudaStream_t st)
 
 extern "C" {
 
+// Tuning hook, not part of the public ABI (tools/k1_probe.py only): selects the TMA ring shape.
+int spc_tune_k1(int variant) {
+  g_k1_variant = variant;
+  return SPC_OK;
+}
+
 size_t spc_mask_words_per_column(int dtype, int layout, int nx, int ny, int nk) {
   if (nx <= 0 || ny <= 0 || nk <= 0 || layout != SPC_LAYOUT_KJI) return 0;
   const long long S = (long long)nx * ny;
   if (fast_path(dtype, S)) {
     const long long slab_bytes = S * (dtype == SPC_F32 ? 4 : 8);
-    return (size_t)((slab_bytes + kChunk - 1) / kChunk) * 32 * nk;
+    return (size_t)((slab_bytes + kSubBytes - 1) / kSubBytes) * 32 * nk;
   }
   return (size_t)((S + 31) / 32) * nk;
 }
@@ -403,7 +475,8 @@ int spc_slab_reduce(spc_handle h, const void* const vol[5], int dtype, int layou
   a.total = a.per_field * SPC_NFIELDS;
   a.S = (int)S;
   a.slab_bytes = (int)(S * (dtype == SPC_F32 ? 4 : 8));
-  a.nch = (a.slab_bytes + kChunk - 1) / kChunk;
+  a.nch = (a.slab_bytes + k1_chunk_bytes(a.slab_bytes) - 1) / k1_chunk_bytes(a.slab_bytes);
+  a.nsub = (a.slab_bytes + kSubBytes - 1) / kSubBytes;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (layout == SPC_LAYOUT_IJK) {
     return dtype == SPC_F32 ? launch_ijk<float>(h, a, ncol, nk, st) : launch_ijk<double>(h, a, ncol, nk, st);

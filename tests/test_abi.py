@@ -49,7 +49,7 @@ def test_struct_sizes_match_header():
     from sp_coupler_b200 import _abi
     assert ctypes.sizeof(_abi.GcmCols) == 16 + 18 * 8        # 3 ints (+pad) + 18 pointers
     assert ctypes.sizeof(_abi.LesForcing) == 23 * 8
-    assert ctypes.sizeof(_abi.LesProf) == 7 * 8 + 4 * 4
+    assert ctypes.sizeof(_abi.LesProf) == 8 * 8 + 4 * 4
     assert ctypes.sizeof(_abi.GcmTend) == 7 * 8
 
 

@@ -1,0 +1,108 @@
+"""Full-size parity (BASELINE.json configs C3 / C4 / C5) through size-independent properties:
+an independent float64 device reduction over ALL columns, exact integer counts, spot columns against
+the CPU oracle on bit-identical host-generated inputs, determinism, sharding invariance and the
+constant-slab identity. Volumes are generated on the device (26.8 GB at C3, 107 GB at C4)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+from oracle import numpy_batched as nb
+from sp_coupler_b200 import synth
+from sp_coupler_b200.constants import LES_FIELDS, TENDENCIES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cpl(cuda_device):
+    from sp_coupler_b200.coupler import Coupler
+    return Coupler(cuda_device)
+
+
+def n(t):
+    return t.detach().cpu().numpy()
+
+
+def _free_gb(dev):
+    free, _ = torch.cuda.mem_get_info(dev)
+    return free / 1e9
+
+
+def _run_config(cpl, dev, ncol, nx, nk, nlev, spots, chunk):
+    need = 5 * ncol * nx * nx * nk * 4 / 1e9
+    if _free_gb(dev) < need * 1.08 + 3:
+        pytest.skip("needs %.0f GB of free HBM" % need)
+    zf, zh = synth.les_grid(nk)
+    gcm = synth.make_gcm_columns(ncol, nlev, seed=44, dtype=np.float32)
+    aux = synth.make_les_aux(ncol, nk, seed=44, dtype=np.float32)
+    vols = synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=44, dtype=torch.float32)
+    S = nx * nx
+    slab = cpl.slab_reduce(vols)
+    # (1) independent float64 reduction + exact counts over ALL columns, chunked to bound memory
+    for c0 in range(0, ncol, chunk):
+        c1 = min(c0 + chunk, ncol)
+        for f, v in enumerate(vols):
+            ref = v[c0:c1].double().sum(dim=(2, 3)) / S
+            err = (slab["prof"][f, c0:c1] - ref).abs().max() / ref.abs().max()
+            assert float(err) <= 1e-12, (LES_FIELDS[f], c0)
+        cnt = (vols[2][c0:c1] > 0).sum(dim=(2, 3), dtype=torch.int32)
+        assert torch.equal(cnt, slab["cnt"][c0:c1])
+    # (2) determinism: a second pass is bit-identical
+    slab2 = cpl.slab_reduce(vols)
+    for k in ("prof", "cnt", "mask"):
+        assert torch.equal(slab[k], slab2[k]), k
+    # (3) sharding invariance: a column sub-range reduces to the same bits as inside the full batch
+    lo, hi = ncol // 4, ncol // 4 + max(ncol // 8, 1)
+    part = cpl.slab_reduce([v[lo:hi] for v in vols])
+    assert torch.equal(part["prof"], slab["prof"][:, lo:hi]) and torch.equal(part["cnt"], slab["cnt"][lo:hi])
+    # (4) whole step on the device, spot columns against the oracle on host-generated inputs
+    d_gcm = {k: torch.from_numpy(v).to(dev) for k, v in gcm.items()}
+    d_aux = {k: torch.from_numpy(v).to(dev) for k, v in aux.items()}
+    d_zf, d_zh = torch.from_numpy(zf).to(dev), torch.from_numpy(zh).to(dev)
+    frc = cpl.gcm_to_les(d_gcm, d_zf, d_zh, slab["prof"], d_aux["PS"], 900.0, 1.0, True, want_bracket=True)
+    tnd = cpl.les_to_gcm(d_gcm, d_zf, d_zh, slab, d_aux, frc["slab_idx"], 900.0, 1.0)
+    for c in spots:
+        g1 = {k: v[c:c + 1] for k, v in gcm.items()}
+        a1 = {k: v[c:c + 1] for k, v in aux.items()}
+        hv = synth.make_les_volumes(g1, zf, nx, nx, seed=44, dtype=np.float32, col0=c)
+        for f, name in enumerate(LES_FIELDS):                      # device generator == host generator
+            assert np.array_equal(n(vols[f][c]), hv[name][0]), name
+        ref = nb.coupling_step(g1, zf, zh, hv, a1, a1["PS"], 900.0, 1.0, 1.0, True)
+        assert np.array_equal(n(slab["cnt"][c]), ref["cnt"][0])
+        assert np.array_equal(n(tnd["cntslab"][c]), ref["cntslab"][0])
+        assert np.array_equal(n(frc["bracket"][c]), ref["forcings"]["bracket"][0])
+        assert np.array_equal(n(frc["slab_idx"][c]), ref["slab_idx"][0])
+        assert int(tnd["start_index"][c]) == int(ref["tendencies"]["start_index"][0])
+        for f, name in enumerate(LES_FIELDS):
+            assert relerr(n(slab["prof"][f, c]), ref["prof"][name][0]) <= 1e-12, name
+        for k in ("f_u", "f_v", "f_thl", "f_qt", "f_ql"):
+            assert relerr(n(frc[k][c]), ref["forcings"][k][0]) <= 1e-4, k
+        for k in TENDENCIES:
+            assert relerr(n(tnd[k][c]), ref["tendencies"][k][0]) <= 1e-4, k
+    # (5) constant-slab identity: mean of a constant slab is that constant, count is all or nothing
+    const = torch.from_numpy(np.random.default_rng(1).normal(0.0, 1.0, (ncol, nk))).to(dev)
+    for f in range(5):
+        cpl.set_les_state(const, 0.0, 0, nx, nx, dtype=torch.float32, out=vols[f])
+    s3 = cpl.slab_reduce(vols, want_mask=False)
+    expect = const.float().double()
+    for f in range(5):
+        assert torch.equal(s3["prof"][f], expect)
+    assert torch.equal(s3["cnt"], torch.where(expect > 0, S, 0).to(torch.int32))
+    del vols
+    torch.cuda.empty_cache()
+
+
+def test_c3_full_size(cpl, cuda_device):
+    """2048 columns, 64x64x160, L91, float32 (26.8 GB)."""
+    _run_config(cpl, cuda_device, 2048, 64, 160, 91, spots=(0, 1023, 2047), chunk=64)
+
+
+def test_c5_shape_per_gpu(cpl, cuda_device):
+    """2048 columns (one GPU's share of 16384), 32x32x160, L137, float32."""
+    _run_config(cpl, cuda_device, 2048, 32, 160, 137, spots=(0, 2047), chunk=256)
+
+
+def test_c4_full_size(cpl, cuda_device):
+    """512 columns, 256x256x160, L91, float32 (107 GB): slabs of 256 KB span 32 TMA chunks."""
+    _run_config(cpl, cuda_device, 512, 256, 160, 91, spots=(511,), chunk=4)

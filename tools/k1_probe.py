@@ -19,6 +19,7 @@ ap.add_argument("--dtype", default="f32")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--layout", default="kji")
 ap.add_argument("--nomask", action="store_true")
+ap.add_argument("--variants", default="0", help="comma list of spc_tune_k1 ring variants to time")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 cpl = Coupler(dev)
@@ -32,21 +33,25 @@ print("generated %.2f GB in %.2fs" % (sum(v.numel() * v.element_size() for v in 
 if a.layout == "ijk":
     vols = [v.permute(0, 3, 2, 1).contiguous() for v in vols]
 nbytes = sum(v.numel() * v.element_size() for v in vols)
-for _ in range(3):
-    s = cpl.slab_reduce(vols, layout=a.layout, want_mask=not a.nomask and a.layout == "kji")
-torch.cuda.synchronize()
-ts = []
-for _ in range(a.iters):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    s = cpl.slab_reduce(vols, layout=a.layout, want_mask=not a.nomask and a.layout == "kji")
-    e1.record()
+from sp_coupler_b200 import _abi
+for variant in [int(x) for x in a.variants.split(",")]:
+    _abi.lib().spc_tune_k1(variant)
+    for _ in range(3):
+        s = cpl.slab_reduce(vols, layout=a.layout, want_mask=not a.nomask and a.layout == "kji")
     torch.cuda.synchronize()
-    ts.append(e0.elapsed_time(e1))
-ts = np.array(ts)
-print("K1 %s ncol=%d %dx%dx%d %s: median %.3f ms min %.3f ms -> %.1f GB/s (median) %.1f GB/s (best); %.0f col/s"
-      % (a.layout, a.ncol, a.nx, a.nx, a.nk, a.dtype, np.median(ts), ts.min(), nbytes / np.median(ts) / 1e6,
-         nbytes / ts.min() / 1e6, a.ncol / np.median(ts) * 1e3))
+    ts = []
+    for _ in range(a.iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s = cpl.slab_reduce(vols, layout=a.layout, want_mask=not a.nomask and a.layout == "kji")
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts = np.array(ts)
+    print("K1 variant %d %s ncol=%d %dx%dx%d %s mask=%s: median %.3f ms min %.3f ms -> %.1f GB/s (median) %.1f GB/s (best); %.0f col/s"
+          % (variant, a.layout, a.ncol, a.nx, a.nx, a.nk, a.dtype, not a.nomask, np.median(ts), ts.min(),
+             nbytes / np.median(ts) / 1e6, nbytes / ts.min() / 1e6, a.ncol / np.median(ts) * 1e3))
+_abi.lib().spc_tune_k1(0)
 # set_les_state write bandwidth
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 prof = torch.zeros((a.ncol, a.nk), dtype=torch.float64, device=dev)
