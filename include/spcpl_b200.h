@@ -177,6 +177,30 @@ int spc_set_les_state(spc_handle h, const double* prof, double amp, uint32_t str
                       int col0, const double* sub, int clamp0, void* vol, int dtype,
                       int ncol, int nx, int ny, int nk, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * spcpl.variability_nudge (spcpl.py:613-744, --qt_forcing variance): per (column, level) find beta with
+ * mean(max(beta*(qt-<qt>)+<qt>-qsat, 0)) = ql_ref by Brent's method (scipy.optimize.brentq restated),
+ * scale the qt fluctuations by it; additive zero-mean noise a*R when beta hits 5; optional constant-T
+ * theta_l correction. KJI layout. qt (and thl) are updated in place.
+ *   status bits: 1 multiplicative root, 2 nudged to barely unsaturated, 4 additive root,
+ *                8 multiplicative bracket failed, 16 additive root not bracketed / R missing. */
+typedef struct {
+  void* qt;              /* in/out [ncol][nk][ny][nx]                                            */
+  const void* qsat;      /* [ncol][nk][ny][nx] saturation humidity (les.get_field("Qsat")), or NULL */
+  const void* qsat_prof; /* [ncol][nk] horizontally uniform qsat, used when qsat == NULL         */
+  void* thl;             /* in/out volume, only with constant_T                                  */
+  const void* ql;        /* volume, only with constant_T                                         */
+  const double* prof;    /* [5][ncol][nk] slab means from spc_slab_reduce (QT and QL rows)       */
+  const void* ql_ref;    /* [ncol][nk] GCM QL on the LES levels (spc_les_forcing.ql_ref)         */
+  const void* presf;     /* [ncol][nk] LES pressure, only with constant_T                        */
+  const double* R;       /* [ncol][ny][nx] zero-mean normal field (spcpl.py:620-621), may be NULL */
+} spc_nudge_io;
+
+int spc_variability_nudge(spc_handle h, const spc_nudge_io* io, int dtype, int ncol, int nx, int ny, int nk,
+                          double DT, int constant_T,
+                          double* beta /* [ncol][nk] */, double* alpha /* log(beta)/DT */,
+                          double* qt_std /* [ncol][nk] */, int32_t* status /* [ncol][nk] */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

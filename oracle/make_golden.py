@@ -37,8 +37,40 @@ def case_inputs(ncol, nlev, nk, seed):
     return zf, zh, gcm, aux, lp, A
 
 
+def nudge_inputs(seed, nx=16, ny=12, nk=24):
+    """Synthetic LES state for spcpl.variability_nudge in the reference's (itot, jtot, ktot) view:
+    levels with every regime (bracketed multiplicative root, unsaturated nudge, beta_max -> additive
+    noise, untouched)."""
+    rng = np.random.default_rng(seed)
+    qt_p = 0.008 * np.exp(-np.arange(nk) / 8.0)
+    qt = qt_p[None, None, :] + 2.5e-5 * rng.uniform(-1, 1, (nx, ny, nk)) * rng.uniform(0.05, 4, nk)[None, None, :]
+    s = rng.uniform(-1.5, 1.5, nk)
+    qsat = qt_p[None, None, :] + 2.5e-5 * s[None, None, :] + 1e-6 * rng.normal(size=(nx, ny, nk))
+    ql = np.maximum(qt - qsat, 0)
+    thl = 290 + rng.normal(size=(nx, ny, nk))
+    qt_av, ql_av = qt.mean(axis=(0, 1)), ql.mean(axis=(0, 1))
+    ql_ref = ql_av * rng.choice([0.0, 0.5, 1.5, 3.0, 40.0], nk) + rng.choice([0, 0, 2e-6], nk)
+    presf = 1e5 * np.exp(-np.arange(nk) * 25 / 7500.)
+    return dict(Qsat=qsat, QT=qt, THL=thl, QL=ql), dict(QT=qt_av, QL=ql_av), presf, ql_ref
+
+
+def make_nudge_golden():
+    kji = lambda a: np.ascontiguousarray(np.transpose(a, (2, 1, 0)))
+    for name, seed, constT in (("ref_nudge", 8, False), ("ref_nudge_constT", 5, True)):
+        f, p, presf, ql_ref = nudge_inputs(seed)
+        r = ref_driver.run_variability_nudge(f, p, presf, ql_ref, 900.0, constT, seed=seed + 100)
+        blob = dict(DT=900.0, constantT=constT, qt=kji(f["QT"]), qsat=kji(f["Qsat"]), thl=kji(f["THL"]), ql=kji(f["QL"]),
+                    qt_av=p["QT"], ql_av=p["QL"], presf=presf, ql_ref=ql_ref, R=np.ascontiguousarray(r["R"].T),
+                    out_qt=kji(r["qt"]), out_beta=r["beta"], out_alpha=r["alpha"], out_qt_std=r["qt_std"])
+        if constT:
+            blob["out_thl"] = kji(r["thl"])
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **blob)
+        print(name, "-> beta", np.round(r["beta"], 3))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    make_nudge_golden()
     for name, ncol, nlev, nk, seed, dt, fl, fg, cons in CASES:
         zf, zh, gcm, aux, lp, A = case_inputs(ncol, nlev, nk, seed)
         out = ref_driver.run_columns(gcm, zf, zh, lp, aux, A, dt, fl, fg, True, conservative=cons)

@@ -111,3 +111,62 @@ def run_columns(gcm, zf, zh, les_prof, aux, A_les, dt, f_les, f_gcm, couple_surf
         rows.append(row)
     keys = rows[0].keys()
     return {k: np.stack([r[k] for r in rows]) for k in keys}
+
+
+class _NudgeLes(object):
+    """LES object with what spcpl.variability_nudge reads (spcpl.py:616-636, 657-658, 732-734)."""
+
+    class _Fields(object):
+        pass
+
+    class _Domain(object):
+        pass
+
+    def __init__(self, fields, profiles, presf, ql_ref, Q):
+        self._f, self._p, self._presf, self._Q = fields, profiles, presf, Q
+        self.ql_ref = Q(ql_ref)
+        self.fields = self._Fields()
+        self.parameters_DOMAIN = self._Domain()
+        self.parameters_DOMAIN.kmax = fields["QT"].shape[2]
+        self.grid_index = 0
+
+    def get_itot(self):
+        return self._f["QT"].shape[0]
+
+    def get_jtot(self):
+        return self._f["QT"].shape[1]
+
+    def get_field(self, name):
+        return self._Q(self._f[name].copy())
+
+    def get_profile(self, name):
+        return self._Q(self._p[name].copy())
+
+    def get_presf(self):
+        return self._Q(self._presf.copy())
+
+
+def run_variability_nudge(fields, profiles, presf, ql_ref, DT, constantT, seed):
+    """Drive the UNMODIFIED reference spcpl.variability_nudge. fields: dict Qsat, QT, THL, QL of
+    (itot, jtot, ktot) float64 arrays (the OMUSE view); profiles: dict QL, QT [ktot].
+    numpy's global RNG is seeded with `seed` right before the call, so R (spcpl.py:620-621) can be
+    regenerated by the caller with the same seed. Returns dict(qt, thl, beta, alpha, qt_std, R)."""
+    sputils, spcpl, spdummy, spio = load_reference()
+    from _q import Q
+    captured = {}
+    spio.write_les_data = lambda les, **kw: captured.update(kw)
+    les = _NudgeLes(fields, profiles, presf, ql_ref, Q)
+    itot, jtot = les.get_itot(), les.get_jtot()
+    np.random.seed(seed)
+    R = np.random.normal(size=(itot, jtot))
+    R -= R.sum() / (itot * jtot)
+    np.random.seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        spcpl.variability_nudge(les, Q(np.float64(DT)), constantT, write=True)
+    out = dict(qt=np.array(les.fields.QT, dtype=np.float64), R=R,
+               beta=np.array(captured["qt_beta"], dtype=np.float64),
+               alpha=np.array(captured["qt_alpha"], dtype=np.float64),
+               qt_std=np.array(captured["qt_std"], dtype=np.float64))
+    if constantT:
+        out["thl"] = np.array(les.fields.THL, dtype=np.float64)
+    return out

@@ -27,6 +27,7 @@ SOURCES = {
     "slab_reduce.cu": [],
     "profiles.cu": ["--fmad=false"],
     "les_state.cu": ["--fmad=false"],
+    "nudge.cu": ["--fmad=false"],
 }
 
 

@@ -305,6 +305,38 @@ class Coupler(object):
         return vol
 
 
+    # ------------------------------------------------------------------ variability nudge
+    def variability_nudge(self, qt, prof, ql_ref, DT, qsat=None, qsat_prof=None, R=None, constant_T=False,
+                          thl=None, ql=None, presf=None):
+        """spcpl.variability_nudge for all columns (spcpl.py:613-744); qt (and thl) [ncol,nk,ny,nx] are
+        updated in place. Returns dict(beta, alpha, qt_std [ncol,nk] f64, status [ncol,nk] i32)."""
+        ncol, nk, ny, nx = qt.shape
+        dtype = qt.dtype
+        self._chk(qt, "qt", dtype)
+        self._chk(prof, "prof", torch.float64, (5, ncol, nk))
+        self._chk(ql_ref, "ql_ref", dtype, (ncol, nk))
+        io = _abi.NudgeIO()
+        io.qt, io.prof, io.ql_ref = qt.data_ptr(), prof.data_ptr(), ql_ref.data_ptr()
+        if qsat is not None:
+            io.qsat = self._chk(qsat, "qsat", dtype, qt.shape).data_ptr()
+        if qsat_prof is not None:
+            io.qsat_prof = self._chk(qsat_prof, "qsat_prof", dtype, (ncol, nk)).data_ptr()
+        if R is not None:
+            io.R = self._chk(R, "R", torch.float64, (ncol, ny, nx)).data_ptr()
+        if constant_T:
+            io.thl = self._chk(thl, "thl", dtype, qt.shape).data_ptr()
+            io.ql = self._chk(ql, "ql", dtype, qt.shape).data_ptr()
+            io.presf = self._chk(presf, "presf", dtype, (ncol, nk)).data_ptr()
+        out = {k: self._empty((ncol, nk), torch.float64) for k in ("beta", "alpha", "qt_std")}
+        out["status"] = self._empty((ncol, nk), torch.int32)
+        _abi.check(self._lib.spc_variability_nudge(self._h, C.byref(io), _DT[dtype], ncol, nx, ny, nk, float(DT),
+                                                   int(bool(constant_T)), _ptr(out["beta"]), _ptr(out["alpha"]),
+                                                   _ptr(out["qt_std"]), _ptr(out["status"]), self._stream()),
+                   "spc_variability_nudge")
+        self.launches += 1
+        return out
+
+
 _default = {}
 
 

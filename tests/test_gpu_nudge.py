@@ -1,0 +1,114 @@
+"""GPU parity of the qt-variability nudging (spc_variability_nudge) against golden vectors of the
+unmodified reference (spcpl.variability_nudge, spcpl.py:613-744) and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, relerr
+from oracle import nudge as onudge
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cpl(cuda_device):
+    from sp_coupler_b200.coupler import Coupler
+    return Coupler(cuda_device)
+
+
+def n(t):
+    return t.detach().cpu().numpy()
+
+
+def prof_of(qt_av, ql_av, dev):
+    """[5][ncol][nk] slab-mean block with the QT and QL rows filled (THL,QT,QL,U,V order)."""
+    p = np.zeros((5,) + qt_av.shape)
+    p[1], p[2] = qt_av, ql_av
+    return torch.from_numpy(p).to(dev)
+
+
+@pytest.mark.parametrize("name", ["ref_nudge", "ref_nudge_constT"])
+def test_nudge_matches_reference_golden(cpl, cuda_device, name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cT = bool(z["constantT"])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)[None]).to(cuda_device)
+    qt, thl = t(z["qt"]), t(z["thl"])
+    out = cpl.variability_nudge(qt, prof_of(z["qt_av"][None], z["ql_av"][None], cuda_device), t(z["ql_ref"]),
+                                float(z["DT"]), qsat=t(z["qsat"]), R=t(z["R"]), constant_T=cT, thl=thl, ql=t(z["ql"]),
+                                presf=t(z["presf"]))
+    assert relerr(n(out["beta"][0]), z["out_beta"]) <= 1e-9
+    assert relerr(n(out["alpha"][0]), z["out_alpha"]) <= 1e-9
+    assert relerr(n(qt[0]) - z["qt"], z["out_qt"] - z["qt"]) <= 1e-6        # relative to the size of the nudge
+    assert relerr(n(qt[0]), z["out_qt"]) <= 1e-12
+    assert relerr(n(out["qt_std"][0]), z["out_qt_std"]) <= 1e-9
+    if cT:
+        assert relerr(n(thl[0]) - z["thl"], z["out_thl"] - z["thl"]) <= 1e-6
+    o = onudge.variability_nudge(z["qt"], z["qsat"], z["qt_av"], z["ql_av"], z["ql_ref"], z["R"], float(z["DT"]), cT,
+                                 thl=z["thl"], ql=z["ql"], presf=z["presf"])
+    assert np.array_equal(n(out["status"][0]), o["status"])                  # same branch on every level
+
+
+def _batch_case(ncol, nk, ny, nx, dtype, seed):
+    rng = np.random.default_rng(seed)
+    qt_p = 0.008 * np.exp(-np.arange(nk) / 8.0)
+    qt = (qt_p[None, :, None, None] + 2.5e-5 * rng.uniform(-1, 1, (ncol, nk, ny, nx)) *
+          rng.uniform(0.05, 4, (ncol, nk))[:, :, None, None]).astype(dtype)
+    qsat_prof = (qt_p[None, :] + 2.5e-5 * rng.uniform(-1.5, 1.5, (ncol, nk))).astype(dtype)
+    ql = np.maximum(qt.astype(np.float64) - qsat_prof.astype(np.float64)[:, :, None, None], 0).astype(dtype)
+    thl = (290 + rng.normal(size=(ncol, nk, ny, nx))).astype(dtype)
+    qt_av = qt.astype(np.float64).mean(axis=(2, 3))
+    ql_av = ql.astype(np.float64).mean(axis=(2, 3))
+    ql_ref = (ql_av * rng.choice([0.0, 0.5, 1.5, 3.0, 40.0], (ncol, nk)) + rng.choice([0, 0, 2e-6], (ncol, nk))).astype(dtype)
+    presf = (1e5 * np.exp(-np.arange(nk) * 25 / 7500.))[None, :].repeat(ncol, 0).astype(dtype)
+    R = rng.normal(size=(ncol, ny, nx))
+    R -= R.mean(axis=(1, 2), keepdims=True)
+    return qt, qsat_prof, ql, thl, qt_av, ql_av, ql_ref, presf, R
+
+
+@pytest.mark.parametrize("ncol,nk,ny,nx,dtype,rtol", [
+    (3, 12, 64, 64, np.float32, 1e-4),       # slab cached in shared memory (32 KB)
+    (2, 6, 64, 64, np.float64, 1e-6),
+    (1, 3, 256, 256, np.float32, 1e-4),      # slab too large for shared memory: L2/global re-read path
+    (2, 5, 10, 7, np.float64, 1e-6),         # ragged
+])
+def test_nudge_batch_matches_oracle(cpl, cuda_device, ncol, nk, ny, nx, dtype, rtol):
+    qt, qsat_prof, ql, thl, qt_av, ql_av, ql_ref, presf, R = _batch_case(ncol, nk, ny, nx, dtype, 11)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    d_qt, d_thl = t(qt), t(thl)
+    out = cpl.variability_nudge(d_qt, prof_of(qt_av, ql_av, cuda_device), t(ql_ref), 900.0, qsat_prof=t(qsat_prof),
+                                R=t(R), constant_T=True, thl=d_thl, ql=t(ql), presf=t(presf))
+    for c in range(ncol):
+        qs = np.broadcast_to(qsat_prof[c].astype(np.float64)[:, None, None], qt[c].shape)
+        o = onudge.variability_nudge(qt[c], qs, qt_av[c], ql_av[c], ql_ref[c].astype(np.float64), R[c], 900.0, True,
+                                     thl=thl[c], ql=ql[c], presf=presf[c].astype(np.float64))
+        assert np.array_equal(n(out["status"][c]), o["status"])
+        assert relerr(n(out["beta"][c]), o["beta"]) <= 1e-9
+        assert relerr(n(d_qt[c]), o["qt"]) <= rtol * 1e-2
+        assert relerr(n(d_qt[c]).astype(np.float64) - qt[c], o["qt"] - qt[c]) <= max(rtol, 2e-3 if dtype == np.float32 else 0)
+        assert relerr(n(out["qt_std"][c]), o["qt_std"]) <= rtol
+        assert relerr(n(d_thl[c]), o["thl"]) <= rtol
+    assert (n(out["status"]) & onudge.ST_MULT).any()
+
+
+def test_nudge_facade(cuda_device):
+    """spcpl.set_les_forcings(..., qt_forcing='variance') route and the batched call agree."""
+    from sp_coupler_b200 import splib, spcpl, nudge
+    splib.initialize(dict(max_num_les=3, les_nx=16, les_ny=16, les_nk=160, gcm_nlev=19, dtype="f64", cplsurf=True,
+                          per_column=False, write_diagnostics=False), device=cuda_device)
+    b = splib.les_batch
+    spcpl.gather_gcm_data(splib.gcm_model, splib.les_models, True)
+    spcpl.set_les_forcings_all(b, 900.0, 1.0, True, firststep=True)
+    b.ql_ref = b.ql_ref + 2e-6                     # make the GCM cloudier than the LES so that levels get nudged
+    R = nudge.zero_mean_normal(b.ncol, b.ny, b.nx, cuda_device, torch.Generator(device=cuda_device).manual_seed(1))
+    qt0 = b.vols[1].clone()
+    out_all = nudge.variability_nudge_all(b, 900.0, False, R=R)
+    qt_all = b.vols[1].clone()
+    assert not torch.equal(qt0, qt_all) and (n(out_all["status"]) != 0).any()
+    b.vols[1].copy_(qt0)
+    for les in splib.les_models:
+        les.ql_ref = b.ql_ref[les.i]
+        o = nudge.variability_nudge(les, 900.0, False, write=False, R=R[les.i:les.i + 1])
+        assert torch.equal(o["beta"][0], out_all["beta"][les.i])
+    assert torch.equal(b.vols[1], qt_all)
