@@ -72,7 +72,8 @@ int spc_destroy(spc_handle h);
  *   prof     out float64 [5][ncol][nk]   mean over the nx*ny horizontal points
  *   cnt      out int32   [ncol][nk]      #{(i,j): (double)ql > ql_thresh}   (may be NULL)
  *   mask     out uint32  [ncol][spc_mask_words_per_column(...)]  per-cell cloud bitmask in an
- *            opaque layout consumed by spc_les_to_gcm for the projected cloud cover (may be NULL)
+ *            opaque layout (one bit per cell; differs between KJI and IJK) consumed by
+ *            spc_les_to_gcm / spc_cloud_fraction for the projected cloud cover (may be NULL)
  */
 size_t spc_mask_words_per_column(int dtype, int layout, int nx, int ny, int nk);
 

@@ -143,7 +143,10 @@ struct K3Args {
   spc_les_prof les;
   spc_gcm_tend o;
   double dt, factor;
-  int nk, conservative, mask_words;  // mask words per (column, level)
+  int nk, conservative;
+  int mask_words;       // KJI: mask words per (column, level); IJK: words per horizontal point
+  int mask_layout, mask_S;
+  size_t mask_per_col;  // mask words per column
 };
 
 // sputils.integral, weighted branch (sputils.py:94-161), a <= b guaranteed by the caller
@@ -208,17 +211,48 @@ __device__ __forceinline__ void project_cloud_mask(const uint32_t* m, const int3
   }
 }
 
+// Same projection for the IJK-layout mask of K1: [S][kw] words per column, bit k%32 of word k/32
+// of horizontal point `row` (the levels of a point are contiguous). One thread per point walks the
+// slabs and tests its bit range; warp-reduced integer counts.
+__device__ __forceinline__ void project_cloud_rows(const uint32_t* m, const int32_t* idx, int S, int kw, int nk, int nlev,
+                                                   int* cslab) {
+  const int S_pad = (S + 31) & ~31;
+  for (int row = threadIdx.x; row < S_pad; row += blockDim.x) {
+    const uint32_t* w = m + (size_t)row * kw;
+    const bool valid = row < S;
+    int k0 = 0;
+    for (int r = 0; r < nlev && k0 < nk; ++r) {  // block-uniform trip count (idx is per column)
+      const int k1 = min(max(__ldg(idx + r), k0), nk);
+      bool any = false;
+      if (valid && k1 > k0) {
+        for (int q = k0 >> 5; q <= (k1 - 1) >> 5; ++q) {
+          const int lo = max(k0 - (q << 5), 0), hi = min(k1 - (q << 5), 32);   // bit range [lo, hi) of word q
+          const uint32_t range = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+          any = any || ((__ldg(w + q) & range) != 0u);
+        }
+      }
+      const int n = __reduce_add_sync(0xffffffffu, any ? 1 : 0);
+      if (n && (threadIdx.x & 31) == 0) atomicAdd(&cslab[r], n);
+      k0 = k1;
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) cloud_fraction_kernel(const uint32_t* mask, const int32_t* slab_idx,
-                                                                  const int32_t* cnt, int mw, int nk, int nlev,
-                                                                  double npts, int32_t* cntslab, T* A) {
+                                                                  const int32_t* cnt, int layout, int mw, int S,
+                                                                  size_t per_col, int nk, int nlev, double npts,
+                                                                  int32_t* cntslab, T* A) {
   extern __shared__ __align__(16) double sm[];
   int* cslab = reinterpret_cast<int*>(sm);
   const int c = blockIdx.x;
   for (int l = threadIdx.x; l < nlev; l += kThreads) cslab[l] = 0;
   __syncthreads();
-  project_cloud_mask(mask + (size_t)c * nk * mw, slab_idx + (size_t)c * nlev, cnt ? cnt + (size_t)c * nk : nullptr, mw, nk,
-                     nlev, cslab);
+  if (layout == SPC_LAYOUT_KJI)
+    project_cloud_mask(mask + (size_t)c * per_col, slab_idx + (size_t)c * nlev, cnt ? cnt + (size_t)c * nk : nullptr, mw, nk,
+                       nlev, cslab);
+  else
+    project_cloud_rows(mask + (size_t)c * per_col, slab_idx + (size_t)c * nlev, S, mw, nk, nlev, cslab);
   __syncthreads();
   for (int l = threadIdx.x; l < nlev; l += kThreads) {
     if (cntslab) cntslab[(size_t)c * nlev + l] = cslab[l];
@@ -291,8 +325,14 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
   // projected cloud cover per GCM slab from the K1 bit mask
   const bool from_mask = (a.les.A == nullptr) && a.les.mask && a.les.slab_idx;
   if (from_mask)
-    project_cloud_mask(a.les.mask + (size_t)c * nk * a.mask_words, a.les.slab_idx + b,
-                       a.les.cnt ? a.les.cnt + (size_t)c * nk : nullptr, a.mask_words, nk, nlev, cslab);
+  {
+    const uint32_t* mc = a.les.mask + (size_t)c * a.mask_per_col;
+    if (a.mask_layout == SPC_LAYOUT_KJI)
+      project_cloud_mask(mc, a.les.slab_idx + b, a.les.cnt ? a.les.cnt + (size_t)c * nk : nullptr, a.mask_words, nk, nlev,
+                         cslab);
+    else
+      project_cloud_rows(mc, a.les.slab_idx + b, a.mask_S, a.mask_words, nk, nlev, cslab);
+  }
   if (threadIdx.x == 0) {
     // start_index = searchsorted(-Zf, -h[-1]) (spcpl.py:498): GCM levels strictly above the LES top.
     // -Zf ascending <=> ZfA descending index; count of Zf > h_top = nlev - upper_bound(ZfA, h_top)
@@ -454,12 +494,14 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   SPC_REQUIRE(!(conservative && (!les->Rhobf || !zh)), SPC_ERR_ARG,
               "spc_les_to_gcm: conservative coarsening needs Rhobf and zh");
   int mw = 0;
+  size_t mask_per_col = 0;
   if (!les->A && les->mask) {
     SPC_REQUIRE(les->slab_idx != nullptr, SPC_ERR_ARG, "spc_les_to_gcm: mask given without slab_idx");
     SPC_REQUIRE(les->nx > 0 && les->ny > 0, SPC_ERR_ARG, "spc_les_to_gcm: mask given without nx, ny");
     const size_t per_col = spc_mask_words_per_column(les->vol_dtype, les->layout, les->nx, les->ny, nk);
     SPC_REQUIRE(per_col > 0, SPC_ERR_UNSUPPORTED, "spc_les_to_gcm: no cloud mask format for this layout/shape");
-    mw = (int)(per_col / nk);
+    mw = les->layout == SPC_LAYOUT_KJI ? (int)(per_col / nk) : (nk + 31) / 32;
+    mask_per_col = per_col;
   }
   if (gcm->ncol == 0) return SPC_OK;
   const size_t smem = ((size_t)2 * gcm->nlev + (size_t)9 * nk + gcm->nlev + 1) * sizeof(double) + (size_t)gcm->nlev * sizeof(int);
@@ -469,6 +511,7 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   a.g = to_ptrs(gcm);
   a.zf = zf; a.zh = zh; a.les = *les; a.o = *out;
   a.dt = dt; a.factor = factor; a.nk = nk; a.conservative = conservative; a.mask_words = mw;
+  a.mask_layout = les->layout; a.mask_S = les->nx * les->ny; a.mask_per_col = mask_per_col;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (gcm->dtype == SPC_F32) les_to_gcm_kernel<float><<<gcm->ncol, kThreads, smem, st>>>(a);
   else les_to_gcm_kernel<double><<<gcm->ncol, kThreads, smem, st>>>(a);
@@ -491,12 +534,15 @@ int spc_cloud_fraction(spc_handle h, const uint32_t* mask, const int32_t* slab_i
   SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_cloud_fraction: nlev=%d too large", nlev);
   spc::DeviceGuard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int mw = (int)(per_col / nk);
+  const int mw = layout == SPC_LAYOUT_KJI ? (int)(per_col / nk) : (nk + 31) / 32;
+  const int S = nx * ny;
   const double npts = (double)nx * (double)ny;
   if (out_dtype == SPC_F32)
-    cloud_fraction_kernel<float><<<ncol, kThreads, smem, st>>>(mask, slab_idx, cnt, mw, nk, nlev, npts, cntslab, (float*)A);
+    cloud_fraction_kernel<float><<<ncol, kThreads, smem, st>>>(mask, slab_idx, cnt, layout, mw, S, per_col, nk, nlev, npts, cntslab,
+                                                               (float*)A);
   else
-    cloud_fraction_kernel<double><<<ncol, kThreads, smem, st>>>(mask, slab_idx, cnt, mw, nk, nlev, npts, cntslab, (double*)A);
+    cloud_fraction_kernel<double><<<ncol, kThreads, smem, st>>>(mask, slab_idx, cnt, layout, mw, S, per_col, nk, nlev, npts, cntslab,
+                                                                (double*)A);
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
 }

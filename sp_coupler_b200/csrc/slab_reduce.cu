@@ -285,15 +285,22 @@ __global__ void __launch_bounds__(256) slab_reduce_generic_kernel(const K1Args a
 // IJK layout ([ncol][nx][ny][nk], k fastest): one CTA per (field, column); thread (r, kk) walks the
 // horizontal points r, r+R, ... of its level(s) kk with coalesced loads along k, then the R partial
 // sums per level are combined through shared memory in a fixed order.
+constexpr int kMaskRows = 4;  // row groups per barrier pair in the masked IJK loop
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(1024) slab_reduce_ijk_kernel(const K1Args a, int nk, int ncol, int nkv, int R) {
   extern __shared__ __align__(128) uint8_t smem[];
   double* ssum = reinterpret_cast<double*>(smem);                  // [R][nk]
   int* scnt = reinterpret_cast<int*>(ssum + (size_t)R * nk);       // [R][nk]
+  const int kw = (nk + 31) >> 5;                                   // mask words per horizontal point
+  uint32_t* rowbits = reinterpret_cast<uint32_t*>(scnt + (size_t)R * nk);  // [kMaskRows*R][kw]
   const int f = blockIdx.x / ncol, c = blockIdx.x - f * ncol;
   const int kk = threadIdx.x % nkv, r = threadIdx.x / nkv;
-  const bool is_ql = (f == SPC_QL) && a.cnt != nullptr;
+  const bool is_ql = (f == SPC_QL) && (a.cnt != nullptr || a.mask != nullptr);
+  const bool do_mask = (f == SPC_QL) && a.mask != nullptr;         // block-uniform
   const T* p = static_cast<const T*>(field_ptr(a, f)) + (size_t)c * a.S * nk;
+  // IJK cloud mask: [ncol][S][kw] words, bit k%32 of word k/32 of horizontal point `row`
+  uint32_t* mcol = do_mask ? a.mask + (size_t)c * a.S * kw : nullptr;
   double acc[VEC];
   int cnt[VEC];
 #pragma unroll
@@ -301,28 +308,67 @@ __global__ void __launch_bounds__(1024) slab_reduce_ijk_kernel(const K1Args a, i
     acc[v] = 0.0;
     cnt[v] = 0;
   }
-  if (r < R) {
-    for (int row = r; row < a.S; row += R) {
-      if constexpr (VEC == 1) {
-        const double d = (double)__ldg(p + (size_t)row * nk + kk);
-        acc[0] += d;
-        cnt[0] += (d > a.thr);
-      } else if constexpr (sizeof(T) == 4) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(p + (size_t)row * nk) + kk);
-        const double d[4] = {(double)q.x, (double)q.y, (double)q.z, (double)q.w};
+  if (do_mask) {
+    for (int i = threadIdx.x; i < R * kMaskRows * kw; i += blockDim.x) rowbits[i] = 0u;
+    __syncthreads();
+  }
+  // one horizontal point: accumulate this thread's VEC levels, return their cloud flags
+  auto point = [&](int row) -> uint32_t {
+    uint32_t flags = 0;
+    if constexpr (VEC == 1) {
+      const double d = (double)__ldg(p + (size_t)row * nk + kk);
+      acc[0] += d;
+      flags = (d > a.thr);
+    } else if constexpr (sizeof(T) == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p + (size_t)row * nk) + kk);
+      const double d[4] = {(double)q.x, (double)q.y, (double)q.z, (double)q.w};
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          acc[v] += d[v];
-          cnt[v] += (d[v] > a.thr);
-        }
-      } else {
-        const double2 q = __ldg(reinterpret_cast<const double2*>(p + (size_t)row * nk) + kk);
-        acc[0] += q.x;
-        acc[1] += q.y;
-        cnt[0] += (q.x > a.thr);
-        cnt[1] += (q.y > a.thr);
+      for (int v = 0; v < 4; ++v) {
+        acc[v] += d[v];
+        flags |= (uint32_t)(d[v] > a.thr) << v;
       }
+    } else {
+      const double2 q = __ldg(reinterpret_cast<const double2*>(p + (size_t)row * nk) + kk);
+      acc[0] += q.x;
+      acc[1] += q.y;
+      flags = (uint32_t)(q.x > a.thr) | ((uint32_t)(q.y > a.thr) << 1);
     }
+    if (is_ql) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) cnt[v] += (flags >> v) & 1u;
+    }
+    return flags;
+  };
+  if (!do_mask) {
+    // streaming loop without block barriers: the compiler keeps several rows of loads in flight
+    if (r < R) {
+#pragma unroll 8
+      for (int row = r; row < a.S; row += R) point(row);
+    }
+  } else {
+    // kMaskRows row groups per barrier pair: loads of 4 rows in flight, 4x fewer block barriers
+    const int step = R * kMaskRows;
+    for (int row0 = 0; row0 < a.S; row0 += step) {                 // block-uniform trip count
+      uint32_t flags[kMaskRows];
+#pragma unroll
+      for (int u = 0; u < kMaskRows; ++u) {
+        const int row = row0 + u * R + r;
+        flags[u] = (r < R && row < a.S) ? point(row) : 0u;
+      }
+      const int k0 = kk * VEC;                                     // VEC divides 32: no word straddling
+#pragma unroll
+      for (int u = 0; u < kMaskRows; ++u)
+        if (flags[u]) atomicOr(&rowbits[(u * R + r) * kw + (k0 >> 5)], flags[u] << (k0 & 31));
+      __syncthreads();
+      for (int i = threadIdx.x; i < step * kw; i += blockDim.x) {
+        const int rr = i / kw;
+        if (row0 + rr < a.S) mcol[(size_t)(row0 + rr) * kw + (i - rr * kw)] = rowbits[i];
+        rowbits[i] = 0u;
+      }
+      __syncthreads();
+    }
+  }
+  if (r < R) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       ssum[(size_t)r * nk + kk * VEC + v] = acc[v];
@@ -338,7 +384,7 @@ __global__ void __launch_bounds__(1024) slab_reduce_ijk_kernel(const K1Args a, i
       n += scnt[(size_t)rr * nk + k];
     }
     a.prof[((size_t)f * ncol + c) * nk + k] = s / (double)a.S;
-    if (is_ql) a.cnt[(size_t)c * nk + k] = n;
+    if (is_ql && a.cnt) a.cnt[(size_t)c * nk + k] = n;
   }
 }
 
@@ -413,10 +459,12 @@ int launch_ijk(spc_handle h, const K1Args& a, int ncol, int nk, cudaStream_t st)
   const int nkv = vec ? nk / V : nk;
   SPC_REQUIRE(nkv <= 1024, SPC_ERR_UNSUPPORTED, "spc_slab_reduce: nk=%d too large for the IJK layout kernel", nk);
   int R = std::max(1, std::min(a.S, 512 / nkv));
-  size_t smem = (size_t)R * nk * (sizeof(double) + sizeof(int));
+  const int kw = (nk + 31) / 32;
+  auto smem_for = [&](int r) { return (size_t)r * nk * (sizeof(double) + sizeof(int)) + (size_t)r * kMaskRows * kw * sizeof(uint32_t); };
+  size_t smem = smem_for(R);
   while (smem > 48 * 1024 && R > 1) {
     --R;
-    smem = (size_t)R * nk * (sizeof(double) + sizeof(int));
+    smem = smem_for(R);
   }
   SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_slab_reduce: nk=%d too large for the IJK layout kernel", nk);
   const int threads = ((nkv * R + 31) / 32) * 32;
@@ -440,8 +488,9 @@ int spc_tune_k1(int variant) {
 }
 
 size_t spc_mask_words_per_column(int dtype, int layout, int nx, int ny, int nk) {
-  if (nx <= 0 || ny <= 0 || nk <= 0 || layout != SPC_LAYOUT_KJI) return 0;
+  if (nx <= 0 || ny <= 0 || nk <= 0 || (layout != SPC_LAYOUT_KJI && layout != SPC_LAYOUT_IJK)) return 0;
   const long long S = (long long)nx * ny;
+  if (layout == SPC_LAYOUT_IJK) return (size_t)S * ((nk + 31) / 32);  // [S][ceil(nk/32)] words per column
   if (fast_path(dtype, S)) {
     const long long slab_bytes = S * (dtype == SPC_F32 ? 4 : 8);
     return (size_t)((slab_bytes + kSubBytes - 1) / kSubBytes) * 32 * nk;
@@ -462,8 +511,6 @@ int spc_slab_reduce(spc_handle h, const void* const vol[5], int dtype, int layou
   if (ncol == 0) return SPC_OK;
   SPC_REQUIRE(vol && prof, SPC_ERR_ARG, "spc_slab_reduce: vol/prof is NULL");
   for (int f = 0; f < SPC_NFIELDS; ++f) SPC_REQUIRE(vol[f] != nullptr, SPC_ERR_ARG, "spc_slab_reduce: vol[%d] is NULL", f);
-  SPC_REQUIRE(!(layout == SPC_LAYOUT_IJK && mask), SPC_ERR_UNSUPPORTED,
-              "spc_slab_reduce: the cloud mask is only produced for the KJI layout");
   spc::DeviceGuard guard(h->device);
   K1Args a;
   a.v0 = vol[0]; a.v1 = vol[1]; a.v2 = vol[2]; a.v3 = vol[3]; a.v4 = vol[4];

@@ -109,7 +109,7 @@ class CouplingPipeline(object):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         self.slab = self.cpl.slab_reduce(self.vols, layout=self.layout, ql_thresh=self.ql_thresh,
-                                         want_mask=(self.layout in ("kji", 0)), out=self.slab)
+                                         want_mask=True, out=self.slab)
         if self.k1_events is not None:
             e1.record()
             self.k1_events.append((e0, e1))

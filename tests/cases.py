@@ -35,7 +35,7 @@ def to_device(case, device):
 def gpu_step(cpl, d, layout=0, dt=900.0, f_les=1.0, f_gcm=1.0, ql_thresh=0.0, diagnostics=True):
     """The device pipeline in the order the driver runs it: K1 -> K2 -> K3."""
     lay = "kji" if layout == 0 else "ijk"
-    slab = cpl.slab_reduce(d["vols"], layout=lay, ql_thresh=ql_thresh, want_mask=(layout == 0))
+    slab = cpl.slab_reduce(d["vols"], layout=lay, ql_thresh=ql_thresh, want_mask=True)
     frc = cpl.gcm_to_les(d["gcm"], d["zf"], d["zh"], slab["prof"], d["aux"]["PS"], dt, f_les, True,
                          diagnostics=diagnostics, want_state=diagnostics, want_bracket=diagnostics)
     tnd = cpl.les_to_gcm(d["gcm"], d["zf"], d["zh"], slab, d["aux"], frc["slab_idx"], dt, f_gcm,

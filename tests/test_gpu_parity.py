@@ -78,22 +78,20 @@ def test_coupling_step_matches_oracle(cpl, cuda_device, ncol, nx, ny, nk, nlev, 
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_ijk_layout_matches_oracle(cpl, cuda_device, dtype):
-    case = cases.host_case(2, 16, 12, 160, 19, dtype, layout=1)
+@pytest.mark.parametrize("shape", [(2, 16, 12, 160, 19), (2, 6, 5, 21, 19), (3, 32, 32, 40, 91)])
+def test_ijk_layout_matches_oracle(cpl, cuda_device, dtype, shape):
+    """[ncol][nx][ny][nk] (OMUSE view, k fastest): whole step incl. the projected cloud cover from
+    the per-point bit mask; odd nk exercises the scalar (non-vectorised) variant."""
+    ncol, nx, ny, nk, nlev = shape
+    case = cases.host_case(ncol, nx, ny, nk, nlev, dtype, layout=1)
     ref = cases.oracle_step(case)
     d = cases.to_device(case, cuda_device)
-    slab = cpl.slab_reduce(d["vols"], layout="ijk", want_mask=False)
-    for i, f in enumerate(LES_FIELDS):
-        assert relerr(n(slab["prof"][i]), ref["prof"][f]) <= 1e-12, f
-    assert np.array_equal(n(slab["cnt"]), ref["cnt"])
-    # odd nk: scalar (non-vectorised) variant
-    case = cases.host_case(2, 6, 5, 21, 19, dtype, layout=1)
-    ref = cases.oracle_step(case)
-    d = cases.to_device(case, cuda_device)
-    slab = cpl.slab_reduce(d["vols"], layout="ijk", want_mask=False)
-    for i, f in enumerate(LES_FIELDS):
-        assert relerr(n(slab["prof"][i]), ref["prof"][f]) <= 1e-12, f
-    assert np.array_equal(n(slab["cnt"]), ref["cnt"])
+    slab, frc, tnd = cases.gpu_step(cpl, d, layout=1)
+    check_step(case, ref, slab, frc, tnd, RTOL[dtype])
+    A, cs = cpl.cloud_fraction(slab, frc["slab_idx"])
+    assert np.array_equal(n(cs), ref["cntslab"])
+    slab2 = cpl.slab_reduce(d["vols"], layout="ijk", want_mask=False)
+    assert np.array_equal(n(slab2["cnt"]), ref["cnt"])
 
 
 @pytest.mark.parametrize("thr", [-1.0, 0.0, 1e-5])
@@ -225,3 +223,37 @@ def test_empty_batch(cpl, cuda_device):
     vols = [torch.empty((0, 20, 8, 8), device=cuda_device) for _ in range(5)]
     slab = cpl.slab_reduce(vols)
     assert slab["prof"].shape == (5, 0, 20)
+
+
+@pytest.mark.parametrize("ncol,nx,ny,nk,dtype", [(3, 40, 40, 24, np.float32), (2, 10, 10, 20, np.float32),
+                                                 (2, 24, 20, 16, np.float64), (2, 64, 64, 21, np.float32)])
+def test_no_out_of_bounds_writes(cpl, cuda_device, ncol, nx, ny, nk, dtype):
+    """compute-sanitizer is closed on this GPU pool, so output buffers are carved out of larger
+    sentinel-filled allocations and the guard bands are checked after the kernels ran."""
+    import torch
+    case = cases.host_case(ncol, nx, ny, nk, 19, dtype)
+    d = cases.to_device(case, cuda_device)
+    td = torch.float32 if dtype == np.float32 else torch.float64
+    G = 64
+
+    def guarded(shape, dt, fill):
+        numel = int(np.prod(shape))
+        buf = torch.full((numel + 2 * G,), fill, dtype=dt, device=cuda_device)
+        return buf, buf[G:G + numel].view(*shape)
+
+    mw = cpl.mask_words_per_column(td, "kji", nx, ny, nk)
+    bp, prof = guarded((5, ncol, nk), torch.float64, -7.0)
+    bc, cnt = guarded((ncol, nk), torch.int32, -7)
+    bm, mask = guarded((ncol, mw), torch.int32, -7)
+    slab = cpl.slab_reduce(d["vols"], out=dict(prof=prof, cnt=cnt, mask=mask))
+    frc = cpl.gcm_to_les(d["gcm"], d["zf"], d["zh"], slab["prof"], d["aux"]["PS"], 900.0, 1.0, True)
+    bt, tend = guarded((ncol, 7, 19), td, -7.0)
+    cpl.les_to_gcm(d["gcm"], d["zf"], d["zh"], slab, d["aux"], frc["slab_idx"], 900.0, 1.0, tend_out=tend)
+    bv, vol = guarded((ncol, nk, ny, nx), td, -7.0)
+    cpl.set_les_state(slab["prof"][0].contiguous(), 0.1, 0, nx, ny, dtype=td, out=vol)
+    torch.cuda.synchronize()
+    for buf, view in ((bp, prof), (bc, cnt), (bm, mask), (bt, tend), (bv, vol)):
+        assert bool((buf[:G] == -7).all()) and bool((buf[-G:] == -7).all())
+    assert not bool((prof == -7.0).any()) and not bool((tend == -7.0).any()) and not bool((vol == -7.0).any())
+    ref = cases.oracle_step(case)
+    assert np.array_equal(n(cnt), ref["cnt"])

@@ -37,13 +37,13 @@ from sp_coupler_b200 import _abi
 for variant in [int(x) for x in a.variants.split(",")]:
     _abi.lib().spc_tune_k1(variant)
     for _ in range(3):
-        s = cpl.slab_reduce(vols, layout=a.layout, want_mask=not a.nomask and a.layout == "kji")
+        s = cpl.slab_reduce(vols, layout=a.layout, want_mask=not a.nomask)
     torch.cuda.synchronize()
     ts = []
     for _ in range(a.iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        s = cpl.slab_reduce(vols, layout=a.layout, want_mask=not a.nomask and a.layout == "kji")
+        s = cpl.slab_reduce(vols, layout=a.layout, want_mask=not a.nomask)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
