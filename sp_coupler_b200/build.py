@@ -68,5 +68,34 @@ def build(force=False, verbose=False):
     return LIB
 
 
+TORCH_LIB = os.path.join(LIBDIR, "spcpl_b200_torch.so")
+
+
+def build_torch_ext(force=False, verbose=False):
+    """The thin PyTorch C++ extension (csrc/torch_ext.cpp -> torch.ops.spcpl_b200.*): plain g++ against
+    torch's headers, linked to libspcpl_b200.so next to it (rpath $ORIGIN). In-tree, no JIT cache."""
+    build(force=force, verbose=verbose)
+    src = os.path.join(CSRC, "torch_ext.cpp")
+    if not (force or _stale(TORCH_LIB, [src, LIB, os.path.join(ROOT, "include", "spcpl_b200.h")])):
+        return TORCH_LIB
+    import torch
+    import torch.utils.cpp_extension as ce
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared",
+           "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+    for inc in ce.include_paths("cuda"):
+        cmd += ["-isystem", inc]
+    cmd += ["-I", os.path.join(ROOT, "include"), src, "-o", TORCH_LIB]
+    for lib in ce.library_paths("cuda"):
+        cmd += ["-L" + lib, "-Wl,-rpath," + lib]
+    cmd += ["-L" + LIBDIR, "-Wl,-rpath,$ORIGIN", "-lspcpl_b200", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda",
+            "-ltorch"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return TORCH_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--torch" in sys.argv:
+        print(build_torch_ext(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -71,3 +71,12 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_torch_extension_builds_and_registers_ops():
+    from sp_coupler_b200 import build, torch_ops
+    assert os.path.exists(build.build_torch_ext())
+    ops = torch_ops.load()
+    assert ops.mask_words_per_column(0, 0, 64, 64, 160) == 64 * 64 * 4 // 4096 * 32 * 160
+    for name in ("slab_reduce", "gcm_to_les", "les_to_gcm"):
+        assert hasattr(ops, name)
