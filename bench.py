@@ -225,7 +225,21 @@ def run_b200(args):
     zf, zh = synth.les_grid(nk)
     gcm_host = synth.make_gcm_columns(ncol, nlev, seed=42 + 2, dtype=ndt, col0=col0, ncol_total=ncol_total)
     aux_host = synth.make_les_aux(ncol, nk, seed=42 + 2, dtype=ndt, col0=col0, ncol_total=ncol_total)
-    pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, tdt, couple_surface=True)
+    gather = args.gather
+    if world > 1 and gather != "nccl":
+        # the fused gather needs NVLink symmetric memory; agree across ranks, else use the NCCL collective
+        try:
+            pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, tdt, couple_surface=True, gather=gather)
+            ok = 1
+        except Exception as e:          # noqa: BLE001
+            sys.stderr.write("rank %d: symmetric-memory gather unavailable (%s); using NCCL all_gather\n" % (rank, e))
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not int(flag.item()):
+            gather = "nccl"
+    if world == 1 or gather == "nccl":
+        pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, tdt, couple_surface=True, gather=gather)
     pipe.staging.fill_host(gcm_host)
     pipe.staging.upload()
     vols = synth.device_les_volumes(cpl, gcm_host, zf, nx, ny, seed=42 + 2, dtype=tdt, col0=col0)
@@ -269,7 +283,7 @@ def run_b200(args):
         pipe.step_device(DT, F_LES, F_GCM)
     e1.record()
     barrier()
-    launches = cpl.launches - l0 + (args.steps if world > 1 else 0)
+    launches = cpl.launches - l0          # our own kernels only (K2, K1, K3 per step); NCCL / barrier kernels not counted
     ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
@@ -311,7 +325,7 @@ def run_b200(args):
         "config": {"workload": workload_name(args.config, ncol), "ncol_total": ncol_total,
                    "storage_dtype": dts, "arithmetic": "f64", "l2": "inputs larger than L2 (%.1f GB of LES volumes per GPU "
                    "streamed once per step; no reuse between steps)" % (bpc * ncol / 1e9),
-                   "parallelism": "columns sharded x%d, tendencies all_gather (NCCL)" % world if world > 1 else "1 GPU",
+                   "parallelism": ("columns sharded x%d, tendencies %s" % (world, "all_gather (NCCL)" if gather == "nccl" else "gathered by K3 itself (%s): NVLink peer stores into symmetric memory + device barrier" % gather)) if world > 1 else "1 GPU",
                    "step": "K2 gcm_to_les -> K1 slab_reduce -> K3 les_to_gcm"},
         "roofline": {"kernel": "slab_reduce_tma_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -345,6 +359,8 @@ def main():
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-cols", type=int, default=4, help="distinct columns per reference worker")
     ap.add_argument("--ref-reps", type=int, default=8, help="passes over them per step")
+    ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p", "p2p-owner"],
+                    help="multi-GPU tendency gather: NCCL all_gather, or fused into K3 (NVLink peer stores)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

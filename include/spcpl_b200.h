@@ -142,7 +142,16 @@ typedef struct {
   int32_t* bracket;     /* optional [ncol][nlev] upper_bound(zf, Zf)-1                          */
   int32_t* bracket_pf;  /* optional [ncol][nk]   upper_bound(Zf[::-1], zf)-1                    */
   int32_t* start_index; /* optional [ncol]       searchsorted(-Zf, -zf[-1]) (spcpl.py:498)      */
+  /* Fused gather (multi-GPU): besides `tend`, the kernel stores this rank's block straight into
+   * n_peers gather buffers [ncol_total][7][nlev] at column offset peer_col0 — peer-mapped device
+   * pointers (NVLink symmetric memory), so the tendencies reach the GCM-owning rank from K3's own
+   * epilogue instead of through a separate collective. tend_peers is a HOST array of n_peers
+   * (<= SPC_MAX_PEERS) device pointers; NULL / 0 disables it. */
+  void* const* tend_peers;
+  int n_peers;
+  int peer_col0;
 } spc_gcm_tend;
+#define SPC_MAX_PEERS 16
 
 int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, const double* zh, int nk,
                    const spc_les_prof* les, double dt, double factor, int conservative,

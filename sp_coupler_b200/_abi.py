@@ -42,7 +42,8 @@ class LesProf(C.Structure):
 
 class GcmTend(C.Structure):
     """struct spc_gcm_tend"""
-    _fields_ = [(n, _vp) for n in ("tend", "t", "A_d", "cntslab", "bracket", "bracket_pf", "start_index")]
+    _fields_ = [(n, _vp) for n in ("tend", "t", "A_d", "cntslab", "bracket", "bracket_pf", "start_index", "tend_peers")] + \
+               [("n_peers", _i), ("peer_col0", _i)]
 
 
 class NudgeIO(C.Structure):

@@ -177,7 +177,7 @@ class Coupler(object):
 
     # ------------------------------------------------------------------ K3
     def les_to_gcm(self, gcm, zf, zh, slab, aux, slab_idx=None, dt=900.0, factor=1.0, conservative=False,
-                   A=None, diagnostics=False, tend_out=None):
+                   A=None, diagnostics=False, tend_out=None, peer_ptrs=None, peer_col0=0):
         """set_gcm_tendencies for all columns (spcpl.py:388-555) incl. the projected cloud fraction.
 
         slab: result of slab_reduce (or a dict with 'prof'); aux: dict QL_ice, T (+Rhobf) [ncol,nk].
@@ -207,6 +207,10 @@ class Coupler(object):
         tend = tend_out if tend_out is not None else self._empty((ncol, 7, nlev), dtype)
         self._chk(tend, "tend", dtype, (ncol, 7, nlev))
         o.tend = tend.data_ptr()
+        if peer_ptrs:       # fused gather: K3 also stores into peer-mapped gather buffers (NVLink)
+            parr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+            o.tend_peers = C.cast(parr, C.c_void_p)
+            o.n_peers, o.peer_col0 = len(peer_ptrs), int(peer_col0)
         res = {"tend": tend}
 
         def alloc(name, shape, dt_=dtype):

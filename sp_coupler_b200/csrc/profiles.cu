@@ -147,6 +147,9 @@ struct K3Args {
   int mask_words;       // KJI: mask words per (column, level); IJK: words per horizontal point
   int mask_layout, mask_S;
   size_t mask_per_col;  // mask words per column
+  void* peers[SPC_MAX_PEERS];  // fused gather targets (peer-mapped gather buffers), see spc_gcm_tend
+  int n_peers;
+  size_t peer_off;      // element offset of this rank's block inside a gather buffer
 };
 
 // sputils.integral, weighted branch (sputils.py:94-161), a <= b guaranteed by the caller
@@ -389,8 +392,12 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
     f[SPC_F_A] = a.factor * (A_d - ld<T>(a.g.A, i)) / ft;                // spcpl.py:526
     const bool above = l < s_start;              // spcpl.py:527-533: f[0:start_index] *= 0
 #pragma unroll
-    for (int n = 0; n < SPC_NTEND; ++n)
-      st<T>(o.tend, ((size_t)c * SPC_NTEND + n) * nlev + l, above ? f[n] * 0.0 : f[n]);
+    for (int n = 0; n < SPC_NTEND; ++n) {
+      const double v = above ? f[n] * 0.0 : f[n];
+      const size_t e = ((size_t)c * SPC_NTEND + n) * nlev + l;
+      st<T>(o.tend, e, v);
+      for (int p = 0; p < a.n_peers; ++p) static_cast<T*>(a.peers[p])[a.peer_off + e] = (T)v;   // NVLink stores
+    }
   }
 }
 
@@ -490,6 +497,10 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   SPC_REQUIRE(zf && les && out && nk >= 1, SPC_ERR_ARG, "spc_les_to_gcm: zf/les/out NULL or nk < 1");
   SPC_REQUIRE(dt != 0.0, SPC_ERR_ARG, "spc_les_to_gcm: dt must be non-zero");
   SPC_REQUIRE(out->tend != nullptr, SPC_ERR_ARG, "spc_les_to_gcm: out->tend is NULL");
+  SPC_REQUIRE(out->n_peers >= 0 && out->n_peers <= SPC_MAX_PEERS && out->peer_col0 >= 0, SPC_ERR_ARG,
+              "spc_les_to_gcm: n_peers=%d / peer_col0=%d out of range", out->n_peers, out->peer_col0);
+  for (int p = 0; out->tend_peers && p < out->n_peers; ++p)
+    SPC_REQUIRE(out->tend_peers[p] != nullptr, SPC_ERR_ARG, "spc_les_to_gcm: tend_peers[%d] is NULL", p);
   SPC_REQUIRE(les->prof && les->QL_ice && les->T, SPC_ERR_ARG, "spc_les_to_gcm: a LES profile pointer is NULL");
   SPC_REQUIRE(!(conservative && (!les->Rhobf || !zh)), SPC_ERR_ARG,
               "spc_les_to_gcm: conservative coarsening needs Rhobf and zh");
@@ -512,6 +523,9 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   a.zf = zf; a.zh = zh; a.les = *les; a.o = *out;
   a.dt = dt; a.factor = factor; a.nk = nk; a.conservative = conservative; a.mask_words = mw;
   a.mask_layout = les->layout; a.mask_S = les->nx * les->ny; a.mask_per_col = mask_per_col;
+  a.n_peers = out->tend_peers ? out->n_peers : 0;
+  for (int p = 0; p < a.n_peers; ++p) a.peers[p] = out->tend_peers[p];
+  a.peer_off = (size_t)out->peer_col0 * SPC_NTEND * gcm->nlev;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (gcm->dtype == SPC_F32) les_to_gcm_kernel<float><<<gcm->ncol, kThreads, smem, st>>>(a);
   else les_to_gcm_kernel<double><<<gcm->ncol, kThreads, smem, st>>>(a);

@@ -94,7 +94,31 @@ class CouplingPipeline(object):
             self.world = torch.distributed.get_world_size(group)
             self.rank = torch.distributed.get_rank(group)
         self.gather = gather and self.world > 1
-        self.tend_all = torch.zeros((ncol * self.world, 7, nlev), dtype=dtype, device=dev) if self.gather else self.tend
+        # gather mode: True / "nccl" = all_gather_into_tensor after K3; "p2p" = fused gather, K3 stores
+        # its block straight into every rank's gather buffer over NVLink (symmetric memory) and a
+        # device-side barrier replaces the collective.
+        #   "p2p-owner": same, but only the GCM-owning rank (rank 0) receives the blocks - all the path needs.
+        self.gather_mode = gather if (self.gather and gather in ("p2p", "p2p-owner")) else "nccl"
+        self.symm = None
+        self.peer_ptrs = None
+        if self.gather and self.gather_mode != "nccl":
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else torch.distributed.group.WORLD
+            # two gather buffers used alternately: while a rank still reads step n's buffer (D2H to the
+            # GCM), its peers may already store step n+1 into the other one; one barrier per step suffices
+            self._p2p = []
+            for _ in range(2):
+                buf = symm_mem.empty((ncol * self.world, 7, nlev), dtype=dtype, device=dev)
+                buf.zero_()
+                hdl = symm_mem.rendezvous(buf, grp)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                if self.gather_mode == "p2p-owner":
+                    ptrs = [ptrs[0]]                      # rank 0 owns the GCM
+                self._p2p.append((buf, hdl, ptrs))
+            self._p2p_step = 0
+            self.tend_all, self.symm, self.peer_ptrs = self._p2p[0]
+        else:
+            self.tend_all = torch.zeros((ncol * self.world, 7, nlev), dtype=dtype, device=dev) if self.gather else self.tend
         self.tend_host = torch.empty(self.tend_all.shape, dtype=dtype, pin_memory=True)
         self.k1_events = None       # optional [(start, end)] CUDA events around K1 (bench roofline)
 
@@ -124,6 +148,14 @@ class CouplingPipeline(object):
 
     def tendencies(self, frc, dt, factor, conservative=False):
         """K3 (set_gcm_tendencies for all columns, spcpl.py:388-555) + the tendency gather."""
+        if self.gather and self.gather_mode != "nccl":
+            self.tend_all, self.symm, self.peer_ptrs = self._p2p[self._p2p_step & 1]
+            self._p2p_step += 1
+            res = self.cpl.les_to_gcm(self.gcm, self.zf, self.zh, self.slab, self.aux, frc["slab_idx"], dt, factor,
+                                      conservative=conservative, tend_out=self.tend, peer_ptrs=self.peer_ptrs,
+                                      peer_col0=self.rank * self.ncol)
+            self.symm.barrier(channel=0)     # every rank's NVLink stores have landed everywhere
+            return res
         res = self.cpl.les_to_gcm(self.gcm, self.zf, self.zh, self.slab, self.aux, frc["slab_idx"], dt, factor,
                                   conservative=conservative, tend_out=self.tend)
         if self.gather:

@@ -50,7 +50,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_abi.GcmCols) == 16 + 18 * 8        # 3 ints (+pad) + 18 pointers
     assert ctypes.sizeof(_abi.LesForcing) == 23 * 8
     assert ctypes.sizeof(_abi.LesProf) == 8 * 8 + 4 * 4
-    assert ctypes.sizeof(_abi.GcmTend) == 7 * 8
+    assert ctypes.sizeof(_abi.GcmTend) == 8 * 8 + 2 * 4
 
 
 def test_no_cpu_fallback():
