@@ -44,8 +44,9 @@ __device__ __forceinline__ double value(const K5Args& a, int c, long long e, uin
   return (double)(T)v;
 }
 
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(256) les_state_kernel(const K5Args a) {
+// Generic path (any slab size): one Philox group per thread iteration, per-element level lookup.
+template <typename T>
+__global__ void __launch_bounds__(256) les_state_generic_kernel(const K5Args a) {
   const long long total = a.ngrp * a.ncol;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(t / a.ngrp);
@@ -55,20 +56,44 @@ __global__ void __launch_bounds__(256) les_state_kernel(const K5Args a) {
     const long long e0 = g * 4;
     T* out = static_cast<T*>(a.vol) + (size_t)c * a.nE;
     const uint32_t x[4] = {r.x, r.y, r.z, r.w};
-    if constexpr (VEC) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (e0 + i < a.nE) out[e0 + i] = (T)value<T>(a, c, e0 + i, x[i]);
+  }
+}
+
+// Fast path (slab elements % 4 == 0, 16-byte aligned volume): blocks walk (column, level) slabs, so the
+// level's profile values are loaded once per slab and no per-element division is needed; each thread
+// produces one Philox group = one 16-byte (float32) or two 16-byte (float64) coalesced stores.
+template <typename T>
+__global__ void __launch_bounds__(256) les_state_slab_kernel(const K5Args a) {
+  const long long nslab = (long long)a.ncol * a.nk;
+  const int gps = (int)(a.S >> 2);  // Philox groups per slab
+  for (long long sl = blockIdx.x; sl < nslab; sl += gridDim.x) {
+    const int c = (int)(sl / a.nk), k = (int)(sl - (long long)c * a.nk);
+    const double base = __ldg(a.prof + sl);
+    const double sub = a.sub ? __ldg(a.sub + sl) : 0.0;
+    T* out = static_cast<T*>(a.vol) + (size_t)sl * a.S;
+    const long long g0 = (long long)k * gps;  // first group of this slab within the column
+    for (int gl = threadIdx.x; gl < gps; gl += blockDim.x) {
+      const long long g = g0 + gl;
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(a.col0 + c), a.stream_id),
+                                    a.seed, 0x5BD1E995u);
+      const uint32_t x[4] = {r.x, r.y, r.z, r.w};
       T v[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = (T)value<T>(a, c, e0 + i, x[i]);
-      if constexpr (sizeof(T) == 4) {
-        *reinterpret_cast<float4*>(out + e0) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-        *reinterpret_cast<double2*>(out + e0) = make_double2(v[0], v[1]);
-        *reinterpret_cast<double2*>(out + e0 + 2) = make_double2(v[2], v[3]);
+      for (int i = 0; i < 4; ++i) {
+        double d = base + a.amp * noise(x[i]);
+        if (a.sub) d = d - sub;
+        if (a.clamp0) d = fmax(d, 0.0);
+        v[i] = (T)d;
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (e0 + i < a.nE) out[e0 + i] = (T)value<T>(a, c, e0 + i, x[i]);
+      if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(out + 4 * gl) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        *reinterpret_cast<double2*>(out + 4 * gl) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(out + 4 * gl + 2) = make_double2(v[2], v[3]);
+      }
     }
   }
 }
@@ -91,16 +116,17 @@ extern "C" int spc_set_les_state(spc_handle h, const double* prof, double amp, u
   a.S = (long long)nx * ny;
   a.nE = a.S * nk;
   a.ngrp = (a.nE + 3) / 4;
-  const bool vec = (a.nE % 4 == 0) && (reinterpret_cast<uintptr_t>(vol) % 16 == 0);
-  const long long total = a.ngrp * ncol;
-  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 16);
+  const bool fast = (a.S % 4 == 0) && (reinterpret_cast<uintptr_t>(vol) % 16 == 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == SPC_F32) {
-    if (vec) les_state_kernel<float, true><<<grid, 256, 0, st>>>(a);
-    else les_state_kernel<float, false><<<grid, 256, 0, st>>>(a);
+  if (fast) {
+    const int grid = (int)std::min<long long>((long long)ncol * nk, (long long)h->num_sms * 8);
+    if (dtype == SPC_F32) les_state_slab_kernel<float><<<grid, 256, 0, st>>>(a);
+    else les_state_slab_kernel<double><<<grid, 256, 0, st>>>(a);
   } else {
-    if (vec) les_state_kernel<double, true><<<grid, 256, 0, st>>>(a);
-    else les_state_kernel<double, false><<<grid, 256, 0, st>>>(a);
+    const long long total = a.ngrp * ncol;
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 16);
+    if (dtype == SPC_F32) les_state_generic_kernel<float><<<grid, 256, 0, st>>>(a);
+    else les_state_generic_kernel<double><<<grid, 256, 0, st>>>(a);
   }
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
