@@ -293,6 +293,29 @@ def run_b200(args):
     # ---- end-to-end leg: host GCM buffers in, host tendencies out, every step ----
     ms_e2e = timed(lambda: pipe.step_host(DT, F_LES, F_GCM), args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
+    # ---- for the record: the same step if the LES volumes lived in HOST memory (they do not) ----
+    host_vol = None
+    if world == 1 and args.host_volume_cols > 0:
+        hc = min(args.host_volume_cols, ncol)
+        hpipe = CouplingPipeline(cpl, zf, zh, hc, nlev, tdt, couple_surface=True)
+        hpipe.staging.fill_host({k: v[:hc] for k, v in gcm_host.items()})
+        hvols_host = [torch.empty((hc,) + tuple(v.shape[1:]), dtype=tdt, pin_memory=True) for v in vols]
+        for hv, v in zip(hvols_host, vols):
+            hv.copy_(v[:hc])
+        hvols_dev = [torch.empty_like(v[:hc]) for v in vols]
+        hpipe.attach_les(hvols_dev, {k: v[:hc].contiguous() for k, v in aux.items()})
+        hpipe.les_profiles()
+
+        def host_volume_step():
+            for dv, hv in zip(hvols_dev, hvols_host):
+                dv.copy_(hv, non_blocking=True)
+            hpipe.step_host(DT, F_LES, F_GCM)
+
+        ms_hv = timed(host_volume_step, max(3, args.steps // 4), 2)
+        host_vol = {"value": hc / (ms_hv * 1e-3), "unit": "columns/s", "columns": hc, "ms_per_step": ms_hv,
+                    "h2d_bytes_per_step": int(sum(h.numel() * h.element_size() for h in hvols_host)) + hpipe.staging.nbytes,
+                    "note": "NOT the design point: LES volumes copied from pinned host memory every step (PCIe-bound)"}
+        del hvols_host, hvols_dev, hpipe
 
     if rank != 0:
         if world > 1:
@@ -334,6 +357,7 @@ def run_b200(args):
         "e2e": {"value": ncol_total / (ms_e2e * 1e-3), "unit": "columns/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
                 "note": "GCM profiles H2D (pinned) + tendencies D2H every step; LES volumes are device-resident LES state"},
+        "e2e_host_volumes": host_vol,
         "gpu_launches": launches,
         "clocks": clocks,
     }
@@ -356,6 +380,8 @@ def main():
     ap.add_argument("--ncol", type=int, default=0, help="override columns per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--host-volume-cols", type=int, default=64,
+                    help="columns of the extra 'volumes in host memory' measurement (0 = skip)")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-cols", type=int, default=4, help="distinct columns per reference worker")
     ap.add_argument("--ref-reps", type=int, default=8, help="passes over them per step")

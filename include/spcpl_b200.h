@@ -138,7 +138,8 @@ typedef struct {
   void* tend;           /* packed [ncol][7][nlev]: f_T,f_SH,f_QL,f_QI,f_U,f_V,f_A              */
   void* t;              /* optional [ncol][nk]  diagnostic temperature (spcpl.py:408-409)       */
   void* A_d;            /* optional [ncol][nlev] LES cloud fraction in GCM order (spcpl.py:404) */
-  int32_t* cntslab;     /* optional [ncol][nlev] projected cloudy-column count, ascending slabs */
+  int32_t* cntslab;     /* [ncol][nlev] projected cloudy-column count, ascending slabs; REQUIRED when the cloud
+                           fraction comes from les->mask (written by the projection kernel, read by K3) */
   int32_t* bracket;     /* optional [ncol][nlev] upper_bound(zf, Zf)-1                          */
   int32_t* bracket_pf;  /* optional [ncol][nk]   upper_bound(Zf[::-1], zf)-1                    */
   int32_t* start_index; /* optional [ncol]       searchsorted(-Zf, -zf[-1]) (spcpl.py:498)      */

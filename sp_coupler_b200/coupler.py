@@ -229,7 +229,7 @@ class Coupler(object):
         _abi.check(self._lib.spc_les_to_gcm(self._h, C.byref(s), _ptr(zf), _ptr(zh), nk, C.byref(lp), float(dt),
                                             float(factor), int(bool(conservative)), C.byref(o), self._stream()),
                    "spc_les_to_gcm")
-        self.launches += 1
+        self.launches += 2 if lp.mask else 1      # cloud projection kernel + tendency kernel
         for i, n in enumerate(TENDENCIES):
             res[n] = tend[:, i, :]
         return res

@@ -144,9 +144,6 @@ struct K3Args {
   spc_gcm_tend o;
   double dt, factor;
   int nk, conservative;
-  int mask_words;       // KJI: mask words per (column, level); IJK: words per horizontal point
-  int mask_layout, mask_S;
-  size_t mask_per_col;  // mask words per column
   void* peers[SPC_MAX_PEERS];  // fused gather targets (peer-mapped gather buffers), see spc_gcm_tend
   int n_peers;
   size_t peer_off;      // element offset of this rank's block inside a gather buffer
@@ -172,44 +169,65 @@ __device__ double integral_w(double a, double b, const double* z, int n, const d
   return (S - Sa - Sb) / (Sw - Swa - Swb);                              // sputils.py:161
 }
 
-// Projected cloud cover per GCM slab from the K1 bit mask of one column: slab r = LES levels
-// [idx[r-1], idx[r]) (idx[-1] := 0, clipped to nk); cslab[r] += number of horizontal points with
-// any cloudy cell in the slab (les.get_cloudfraction(indices), spcpl.py:28,765). The mask layout
-// is opaque but identical for every level, so OR over k then popcount is layout-independent.
-// `cnt` (optional, the per-level counts of K1) lets cloud-free levels be skipped without touching
-// their mask words. cslab must be zeroed by the caller; results are exact integers.
-__device__ __forceinline__ void project_cloud_mask(const uint32_t* m, const int32_t* idx, const int32_t* cnt, int mw,
-                                                   int nk, int nlev, int* cslab) {
-  constexpr int B = 8;  // levels fetched per batch: 8 independent loads in flight per thread
-  const int mw_pad = (mw + 31) & ~31;  // warp-uniform trip count so that the warp reductions are full
-  for (int w = threadIdx.x; w < mw_pad; w += blockDim.x) {
-    const bool valid = w < mw;
-    int r = 0;
-    int kend = min(max(__ldg(idx), 0), nk);  // exclusive end of slab r (monotone, clipped)
-    uint32_t acc = 0;
-    for (int kb = 0; kb < nk && r < nlev; kb += B) {
-      uint32_t v[B];
+// ---- projected cloud cover per GCM slab (les.get_cloudfraction(indices), spcpl.py:28,765) ----------
+// Slab r of a column covers the LES levels [k0, k1), k1 = min(max(idx[0..r]), nk), k0 likewise for r-1
+// (idx = searchsorted(zh, Zh, 'right')[:-1][::-1], spcpl.py:26,764, made monotone and clipped).
+// KJI mask: one block per column, ONE WARP per slab. The mask layout is opaque but identical for every
+// level, so the warp ORs the slab's levels word by word (lane <-> word, 4 levels x 4 word segments = 16
+// independent loads in flight), popcounts, and writes one exact integer; levels whose K1 count is zero
+// are skipped without touching their mask words. No atomics, no dependent load chain.
+template <typename T>
+__global__ void __launch_bounds__(256) cloud_project_kji_kernel(const uint32_t* mask, const int32_t* slab_idx,
+                                                                const int32_t* cnt, int mw, int nk, int nlev, double npts,
+                                                                int32_t* cntslab, T* A) {
+  constexpr int KB = 4, SEG = 4;
+  extern __shared__ __align__(16) double sm[];
+  int* sidx = reinterpret_cast<int*>(sm);  // [nlev] slab_idx of this column
+  int* kend = sidx + nlev;                 // [nlev] exclusive end level of every slab
+  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int r = threadIdx.x; r < nlev; r += blockDim.x) sidx[r] = __ldg(slab_idx + (size_t)c * nlev + r);
+  __syncthreads();
+  for (int r = threadIdx.x; r < nlev; r += blockDim.x) {
+    int m = 0;
+    for (int i = 0; i <= r; ++i) m = max(m, sidx[i]);
+    kend[r] = min(m, nk);
+  }
+  __syncthreads();
+  const uint32_t* m = mask + (size_t)c * nk * mw;
+  const int32_t* cn = cnt ? cnt + (size_t)c * nk : nullptr;
+  for (int r = warp; r < nlev; r += nwarps) {
+    const int k0 = r ? kend[r - 1] : 0, k1 = kend[r];
+    int n = 0;
+    if (k1 > k0) {
+      for (int w0 = 0; w0 < mw; w0 += 32 * SEG) {
+        uint32_t acc[SEG];
 #pragma unroll
-      for (int i = 0; i < B; ++i) {
-        const int k = kb + i;
-        const bool live = valid && k < nk && (cnt == nullptr || __ldg(cnt + k) != 0);
-        v[i] = live ? __ldg(m + (size_t)k * mw + w) : 0u;
-      }
+        for (int sg = 0; sg < SEG; ++sg) acc[sg] = 0u;
+        for (int kb = k0; kb < k1; kb += KB) {
+          uint32_t v[KB][SEG];
 #pragma unroll
-      for (int i = 0; i < B; ++i) {
-        const int k = kb + i;
-        while (r < nlev && k >= kend) {  // close slab r (possibly empty), open the next one
-          const int n = __reduce_add_sync(0xffffffffu, __popc(acc));
-          if (n && (threadIdx.x & 31) == 0) atomicAdd(&cslab[r], n);
-          acc = 0;
-          if (++r < nlev) kend = min(max(__ldg(idx + r), kend), nk);
+          for (int j = 0; j < KB; ++j) {
+            const int k = kb + j;
+            const bool live = k < k1 && (cn == nullptr || __ldg(cn + k) != 0);
+#pragma unroll
+            for (int sg = 0; sg < SEG; ++sg) {
+              const int w = w0 + sg * 32 + lane;
+              v[j][sg] = (live && w < mw) ? __ldg(m + (size_t)k * mw + w) : 0u;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < KB; ++j)
+#pragma unroll
+            for (int sg = 0; sg < SEG; ++sg) acc[sg] |= v[j][sg];
         }
-        if (r < nlev) acc |= v[i];
+#pragma unroll
+        for (int sg = 0; sg < SEG; ++sg) n += __popc(acc[sg]);
       }
+      n = __reduce_add_sync(0xffffffffu, n);
     }
-    if (r < nlev) {  // slab that runs to the LES top
-      const int n = __reduce_add_sync(0xffffffffu, __popc(acc));
-      if (n && (threadIdx.x & 31) == 0) atomicAdd(&cslab[r], n);
+    if (lane == 0) {
+      if (cntslab) cntslab[(size_t)c * nlev + r] = n;
+      if (A) A[(size_t)c * nlev + r] = (T)((double)n / npts);
     }
   }
 }
@@ -241,26 +259,43 @@ __device__ __forceinline__ void project_cloud_rows(const uint32_t* m, const int3
   }
 }
 
+// IJK mask: one block per column (project_cloud_rows above).
 template <typename T>
-__global__ void __launch_bounds__(kThreads) cloud_fraction_kernel(const uint32_t* mask, const int32_t* slab_idx,
-                                                                  const int32_t* cnt, int layout, int mw, int S,
-                                                                  size_t per_col, int nk, int nlev, double npts,
-                                                                  int32_t* cntslab, T* A) {
+__global__ void __launch_bounds__(kThreads) cloud_project_ijk_kernel(const uint32_t* mask, const int32_t* slab_idx, int kw, int S,
+                                                                     size_t per_col, int nk, int nlev, double npts,
+                                                                     int32_t* cntslab, T* A) {
   extern __shared__ __align__(16) double sm[];
   int* cslab = reinterpret_cast<int*>(sm);
   const int c = blockIdx.x;
   for (int l = threadIdx.x; l < nlev; l += kThreads) cslab[l] = 0;
   __syncthreads();
-  if (layout == SPC_LAYOUT_KJI)
-    project_cloud_mask(mask + (size_t)c * per_col, slab_idx + (size_t)c * nlev, cnt ? cnt + (size_t)c * nk : nullptr, mw, nk,
-                       nlev, cslab);
-  else
-    project_cloud_rows(mask + (size_t)c * per_col, slab_idx + (size_t)c * nlev, S, mw, nk, nlev, cslab);
+  project_cloud_rows(mask + (size_t)c * per_col, slab_idx + (size_t)c * nlev, S, kw, nk, nlev, cslab);
   __syncthreads();
   for (int l = threadIdx.x; l < nlev; l += kThreads) {
     if (cntslab) cntslab[(size_t)c * nlev + l] = cslab[l];
     if (A) A[(size_t)c * nlev + l] = (T)((double)cslab[l] / npts);
   }
+}
+
+// Launches the projection for either mask layout (shared by spc_cloud_fraction and spc_les_to_gcm).
+template <typename T>
+int launch_cloud_projection(spc_handle h, const uint32_t* mask, const int32_t* slab_idx, const int32_t* cnt, int vol_dtype,
+                            int layout, int nx, int ny, int nk, int ncol, int nlev, int32_t* cntslab, T* A, cudaStream_t st) {
+  const size_t per_col = spc_mask_words_per_column(vol_dtype, layout, nx, ny, nk);
+  SPC_REQUIRE(per_col > 0, SPC_ERR_UNSUPPORTED, "no cloud mask format for this layout/shape");
+  const double npts = (double)nx * (double)ny;
+  if (layout == SPC_LAYOUT_KJI) {
+    const size_t smem = (size_t)2 * nlev * sizeof(int);
+    SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "nlev=%d too large", nlev);
+    cloud_project_kji_kernel<T><<<ncol, 256, smem, st>>>(mask, slab_idx, cnt, (int)(per_col / nk), nk, nlev, npts, cntslab, A);
+  } else {
+    const size_t smem = (size_t)nlev * sizeof(int);
+    SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "nlev=%d too large", nlev);
+    cloud_project_ijk_kernel<T><<<ncol, kThreads, smem, st>>>(mask, slab_idx, (nk + 31) / 32, nx * ny, per_col, nk, nlev, npts,
+                                                             cntslab, A);
+  }
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
 }
 
 template <typename T>
@@ -280,7 +315,6 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
   double* v_d = u_d + nk;
   double* rho = v_d + nk;        // [nk]   (conservative only)
   double* ZhD = rho + nk;        // [nlev+1] descending half-level heights (conservative only)
-  int* cslab = reinterpret_cast<int*>(ZhD + nlev + 1);  // [nlev]
   __shared__ int s_start;
 
   const size_t b = (size_t)c * nlev, bh = (size_t)c * (nlev + 1);
@@ -291,8 +325,9 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
   for (int l = threadIdx.x; l < nlev; l += kThreads) {
     ZfA[nlev - 1 - l] = (ld<T>(a.g.Zgfull, b + l) - zs) / grav;         // les.gcm_Zf, spcpl.py:198,390
     PfA[nlev - 1 - l] = ld<T>(a.g.Pfull, b + l);
-    cslab[l] = 0;
   }
+  // projected cloud counts were written to o.cntslab by the projection kernel launched just before
+  const bool from_mask = (a.les.A == nullptr) && a.les.mask && o.cntslab;
   if (a.conservative)
     for (int l = threadIdx.x; l <= nlev; l += kThreads) ZhD[l] = (ld<T>(a.g.Zghalf, bh + l) - zs) / grav;
   for (int k = threadIdx.x; k < nk; k += kThreads) {
@@ -325,17 +360,6 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
     }
   }
 
-  // projected cloud cover per GCM slab from the K1 bit mask
-  const bool from_mask = (a.les.A == nullptr) && a.les.mask && a.les.slab_idx;
-  if (from_mask)
-  {
-    const uint32_t* mc = a.les.mask + (size_t)c * a.mask_per_col;
-    if (a.mask_layout == SPC_LAYOUT_KJI)
-      project_cloud_mask(mc, a.les.slab_idx + b, a.les.cnt ? a.les.cnt + (size_t)c * nk : nullptr, a.mask_words, nk, nlev,
-                         cslab);
-    else
-      project_cloud_rows(mc, a.les.slab_idx + b, a.mask_S, a.mask_words, nk, nlev, cslab);
-  }
   if (threadIdx.x == 0) {
     // start_index = searchsorted(-Zf, -h[-1]) (spcpl.py:498): GCM levels strictly above the LES top.
     // -Zf ascending <=> ZfA descending index; count of Zf > h_top = nlev - upper_bound(ZfA, h_top)
@@ -351,9 +375,8 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
     const int r = nlev - 1 - l;                  // ascending slab index of GCM level l
     double A_d;                                  // profile["A"][::-1], spcpl.py:404
     if (a.les.A) A_d = ld<T>(a.les.A, b + r);
-    else if (from_mask) A_d = (double)cslab[r] / npts;
+    else if (from_mask) A_d = (double)o.cntslab[b + r] / npts;   // cntslab is in ascending slab order
     else A_d = 0.0;
-    if (o.cntslab) o.cntslab[i] = from_mask ? cslab[l] : -1;   // ascending order, as get_cloudfraction returns
     st<T>(o.A_d, i, A_d);
     const double x = ZfA[r];                     // Zf[l]
     double tl, qtl, qll, qlwl, qlil, ul, vl;
@@ -504,29 +527,30 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   SPC_REQUIRE(les->prof && les->QL_ice && les->T, SPC_ERR_ARG, "spc_les_to_gcm: a LES profile pointer is NULL");
   SPC_REQUIRE(!(conservative && (!les->Rhobf || !zh)), SPC_ERR_ARG,
               "spc_les_to_gcm: conservative coarsening needs Rhobf and zh");
-  int mw = 0;
-  size_t mask_per_col = 0;
-  if (!les->A && les->mask) {
+  const bool project = !les->A && les->mask;
+  if (project) {
     SPC_REQUIRE(les->slab_idx != nullptr, SPC_ERR_ARG, "spc_les_to_gcm: mask given without slab_idx");
     SPC_REQUIRE(les->nx > 0 && les->ny > 0, SPC_ERR_ARG, "spc_les_to_gcm: mask given without nx, ny");
-    const size_t per_col = spc_mask_words_per_column(les->vol_dtype, les->layout, les->nx, les->ny, nk);
-    SPC_REQUIRE(per_col > 0, SPC_ERR_UNSUPPORTED, "spc_les_to_gcm: no cloud mask format for this layout/shape");
-    mw = les->layout == SPC_LAYOUT_KJI ? (int)(per_col / nk) : (nk + 31) / 32;
-    mask_per_col = per_col;
+    SPC_REQUIRE(out->cntslab != nullptr, SPC_ERR_ARG,
+                "spc_les_to_gcm: out->cntslab is required when the cloud fraction comes from the mask");
   }
   if (gcm->ncol == 0) return SPC_OK;
-  const size_t smem = ((size_t)2 * gcm->nlev + (size_t)9 * nk + gcm->nlev + 1) * sizeof(double) + (size_t)gcm->nlev * sizeof(int);
+  const size_t smem = ((size_t)2 * gcm->nlev + (size_t)9 * nk + gcm->nlev + 1) * sizeof(double);
   SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_les_to_gcm: nlev=%d, nk=%d too large", gcm->nlev, nk);
   spc::DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (project) {  // projected cloud counts per GCM slab, consumed by the tendency kernel right after
+    rc = launch_cloud_projection<float>(h, les->mask, les->slab_idx, les->cnt, les->vol_dtype, les->layout, les->nx, les->ny,
+                                        nk, gcm->ncol, gcm->nlev, out->cntslab, nullptr, st);
+    if (rc) return rc;
+  }
   K3Args a;
   a.g = to_ptrs(gcm);
   a.zf = zf; a.zh = zh; a.les = *les; a.o = *out;
-  a.dt = dt; a.factor = factor; a.nk = nk; a.conservative = conservative; a.mask_words = mw;
-  a.mask_layout = les->layout; a.mask_S = les->nx * les->ny; a.mask_per_col = mask_per_col;
+  a.dt = dt; a.factor = factor; a.nk = nk; a.conservative = conservative;
   a.n_peers = out->tend_peers ? out->n_peers : 0;
   for (int p = 0; p < a.n_peers; ++p) a.peers[p] = out->tend_peers[p];
   a.peer_off = (size_t)out->peer_col0 * SPC_NTEND * gcm->nlev;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (gcm->dtype == SPC_F32) les_to_gcm_kernel<float><<<gcm->ncol, kThreads, smem, st>>>(a);
   else les_to_gcm_kernel<double><<<gcm->ncol, kThreads, smem, st>>>(a);
   SPC_CUDA(cudaGetLastError());
@@ -542,23 +566,11 @@ int spc_cloud_fraction(spc_handle h, const uint32_t* mask, const int32_t* slab_i
   SPC_REQUIRE(out_dtype == SPC_F32 || out_dtype == SPC_F64, SPC_ERR_ARG, "spc_cloud_fraction: bad out_dtype %d", out_dtype);
   if (ncol == 0) return SPC_OK;
   SPC_REQUIRE(mask && slab_idx && (cntslab || A), SPC_ERR_ARG, "spc_cloud_fraction: NULL pointer");
-  const size_t per_col = spc_mask_words_per_column(vol_dtype, layout, nx, ny, nk);
-  SPC_REQUIRE(per_col > 0, SPC_ERR_UNSUPPORTED, "spc_cloud_fraction: no cloud mask format for this layout/shape");
-  const size_t smem = (size_t)nlev * sizeof(int);
-  SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_cloud_fraction: nlev=%d too large", nlev);
   spc::DeviceGuard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int mw = layout == SPC_LAYOUT_KJI ? (int)(per_col / nk) : (nk + 31) / 32;
-  const int S = nx * ny;
-  const double npts = (double)nx * (double)ny;
   if (out_dtype == SPC_F32)
-    cloud_fraction_kernel<float><<<ncol, kThreads, smem, st>>>(mask, slab_idx, cnt, layout, mw, S, per_col, nk, nlev, npts, cntslab,
-                                                               (float*)A);
-  else
-    cloud_fraction_kernel<double><<<ncol, kThreads, smem, st>>>(mask, slab_idx, cnt, layout, mw, S, per_col, nk, nlev, npts, cntslab,
-                                                                (double*)A);
-  SPC_CUDA(cudaGetLastError());
-  return SPC_OK;
+    return launch_cloud_projection<float>(h, mask, slab_idx, cnt, vol_dtype, layout, nx, ny, nk, ncol, nlev, cntslab, (float*)A, st);
+  return launch_cloud_projection<double>(h, mask, slab_idx, cnt, vol_dtype, layout, nx, ny, nk, ncol, nlev, cntslab, (double*)A, st);
 }
 
 int spc_interp(spc_handle h, int dtype, const void* x, int x_batched, const void* xp, const void* fp, int nb, int nx,
