@@ -257,3 +257,41 @@ def test_no_out_of_bounds_writes(cpl, cuda_device, ncol, nx, ny, nk, dtype):
     assert not bool((prof == -7.0).any()) and not bool((tend == -7.0).any()) and not bool((vol == -7.0).any())
     ref = cases.oracle_step(case)
     assert np.array_equal(n(cnt), ref["cnt"])
+
+
+def test_c_abi_status_codes(cuda_device):
+    """Raw C-ABI calls (ctypes, no wrapper): status codes and spc_last_error() as documented in
+    include/spcpl_b200.h: 0 ok, <0 invalid argument / alignment / unsupported, message set."""
+    import ctypes as C
+    import torch
+    from sp_coupler_b200 import _abi
+    L = _abi.lib()
+    h = C.c_void_p()
+    assert L.spc_create(C.byref(h), cuda_device.index) == 0
+    assert L.spc_create(C.byref(C.c_void_p()), 9999) == -1 and b"out of range" in L.spc_last_error()
+    nk, ny, nx = 4, 16, 16
+    vols = [torch.zeros((1, nk, ny, nx), device=cuda_device) for _ in range(5)]
+    prof = torch.zeros((5, 1, nk), dtype=torch.float64, device=cuda_device)
+    arr = (C.c_void_p * 5)(*[v.data_ptr() for v in vols])
+    call = lambda a, dtype=0, layout=0, handle=h, p=prof.data_ptr(): L.spc_slab_reduce(
+        handle, a, dtype, layout, 1, nx, ny, nk, 0.0, C.c_void_p(p), None, None, None)
+    assert call(arr) == 0
+    assert call(arr, dtype=7) == _abi_code("SPC_ERR_ARG") and b"dtype" in L.spc_last_error()
+    assert call(arr, layout=5) == -1
+    assert call(arr, p=0) == -1 and b"NULL" in L.spc_last_error()
+    assert call(arr, handle=None) == -4                                       # SPC_ERR_HANDLE
+    bad = (C.c_void_p * 5)(*[v.data_ptr() + (4 if i == 2 else 0) for i, v in enumerate(vols)])
+    assert call(bad) == -2 and b"16-byte aligned" in L.spc_last_error()       # SPC_ERR_ALIGN (TMA bulk path)
+    nullv = (C.c_void_p * 5)(vols[0].data_ptr(), None, vols[2].data_ptr(), vols[3].data_ptr(), vols[4].data_ptr())
+    assert call(nullv) == -1
+    torch.cuda.synchronize()
+    assert L.spc_destroy(h) == 0
+    assert L.spc_destroy(None) == -4
+
+
+def _abi_code(name):
+    import re
+    import os
+    import conftest
+    src = open(os.path.join(conftest.ROOT, "include", "spcpl_b200.h")).read()
+    return int(re.search(name + r"\s*=\s*(-?\d+)", src).group(1))
