@@ -69,6 +69,46 @@ class GcmStaging(object):
         return self.dev
 
 
+class GcmScatter(object):
+    """Multi-GPU form of gather_gcm_data (spcpl.py:55-86): the rank that owns the GCM packs every
+    rank's GcmStaging block into one pinned buffer, uploads it once, and one scatter over the process
+    group (NCCL / NVLink on GPUs, gloo on CPU tensors in the tests) delivers each rank's block straight
+    into its staging device buffer. Equal column counts per rank."""
+
+    def __init__(self, staging, world, rank, owner=0, group=None, device=None, pin=True):
+        self.staging, self.world, self.rank, self.owner, self.group = staging, world, rank, owner, group
+        self.per_rank = staging.dev_buf.numel()
+        self.host_all = self.dev_all = None
+        if rank == owner:
+            self.host_all = torch.empty(world * self.per_rank, dtype=staging.dtype,
+                                        pin_memory=pin and torch.cuda.is_available())
+            self.dev_all = torch.empty(world * self.per_rank, dtype=staging.dtype,
+                                       device=device if device is not None else staging.dev_buf.device)
+
+    def fill_host(self, gcm_all):
+        """Owner only. gcm_all: dict of [world*ncol, ...] host arrays in global column order."""
+        st, ncol = self.staging, self.staging.ncol
+        for r in range(self.world):
+            base = r * self.per_rank
+            off = 0
+            for n, h in st.host.items():
+                cnt = h.numel()
+                src = gcm_all[n][r * ncol:(r + 1) * ncol]
+                src = src if isinstance(src, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(src))
+                self.host_all[base + off:base + off + cnt].view(h.shape).copy_(src)
+                off += cnt
+
+    def scatter(self):
+        """All ranks. Returns the rank's device views (staging.dev)."""
+        if self.rank == self.owner:
+            self.dev_all.copy_(self.host_all, non_blocking=True)
+            chunks = list(self.dev_all.chunk(self.world))
+            torch.distributed.scatter(self.staging.dev_buf, scatter_list=chunks, src=self.owner, group=self.group)
+        else:
+            torch.distributed.scatter(self.staging.dev_buf, src=self.owner, group=self.group)
+        return self.staging.dev
+
+
 class CouplingPipeline(object):
     """State + step of the GPU coupling path for this rank's columns."""
 

@@ -72,6 +72,8 @@ def gather_gcm_data(gcm, les_models, couple_surface, output_column_indices=None,
     log.info("Fetching gcm data took %d s" % (time.time() - start))
     n = len(les_models)
     batch = getattr(les_models[0], "batch", None) if n else None
+    if batch is not None and batch.pipe.world > 1:
+        raise RuntimeError("columns are sharded over ranks: use gather_gcm_data_sharded")
     if batch is not None and n == batch.ncol and all(getattr(l, "batch", None) is batch and l.i == i
                                                      for i, l in enumerate(les_models)):
         st = batch.pipe.staging
@@ -108,6 +110,30 @@ def gather_gcm_data(gcm, les_models, couple_surface, output_column_indices=None,
                                    QT=d["QT"][j], A=g["A"][j])
             if couple_surface:
                 spio.write_netCDF_data(col, z0m=d["z0m"][j], z0h=d["z0h"][j], wthl=d["wthl"][j], wqt=d["wqt"][j])
+
+
+def gather_gcm_data_sharded(gcm, batch, couple_surface=True):
+    """gather_gcm_data when the SP columns are sharded over GPUs (one process per GPU): the rank that
+    owns the GCM fetches the profiles of ALL columns (spcpl.py:62-75), packs them per rank, uploads once,
+    and a scatter over NVLink delivers every rank's block into its staging buffer; then the per-LES
+    attributes are views of the device arrays as in the single-GPU path (spcpl.py:81-86)."""
+    from .pipeline import GcmScatter
+    pipe = batch.pipe
+    if getattr(batch, "_scatter", None) is None:
+        batch._scatter = GcmScatter(pipe.staging, pipe.world, pipe.rank, owner=0, group=pipe.group)
+    if pipe.rank == 0:
+        cols = batch.all_grid_indices
+        data = {v: gcm.get_profile_fields(v, cols) for v in gcm_vars}
+        data.update({v: gcm.get_surface_field(v, cols) for v in surf_vars})
+        batch._scatter.fill_host(data)
+    dev = batch._scatter.scatter()
+    for i, les in enumerate(batch.models):
+        for v in gcm_vars:
+            setattr(les, v, dev[v][i])
+        if couple_surface:
+            for v in surf_vars:
+                setattr(les, v, dev[v][i])
+    return dev
 
 
 def convert_surface_fluxes(les):

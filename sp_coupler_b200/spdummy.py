@@ -160,17 +160,17 @@ class gpu_les_batch(object):
     """All local LES models: five [ncol][nk][ny][nx] volumes + LES-internal profiles in HBM."""
 
     def __init__(self, ncol, nlev, nx=64, ny=64, nk=160, dz=25.0, dtype=torch.float32, device=None, seed=42,
-                 col0=0, couple_surface=True, group=None):
+                 col0=0, couple_surface=True, group=None, gather=True, ncol_total=None):
         self.cpl = default_coupler(device)
         self.ncol, self.nlev, self.nx, self.ny, self.nk, self.dtype = ncol, nlev, nx, ny, nk, dtype
         self.seed, self.col0 = seed, col0
         self.zf_host, self.zh_host = synth.les_grid(nk, dz)
         self.pipe = CouplingPipeline(self.cpl, self.zf_host, self.zh_host, ncol, nlev, dtype, couple_surface,
-                                     group=group)
+                                     group=group, gather=gather)
         dev = self.cpl.device
         self.vols = [torch.zeros((ncol, nk, ny, nx), dtype=dtype, device=dev) for _ in LES_FIELDS]
         ndt = np.float32 if dtype == torch.float32 else np.float64
-        aux = synth.make_les_aux(ncol, nk, seed=seed, dtype=ndt, col0=col0)
+        aux = synth.make_les_aux(ncol, nk, seed=seed, dtype=ndt, col0=col0, ncol_total=ncol_total)
         self.aux = {k: torch.from_numpy(v).to(dev) for k, v in aux.items()}
         self.pipe.attach_les(self.vols, self.aux)
         z = lambda *s: torch.zeros(s, dtype=dtype, device=dev)

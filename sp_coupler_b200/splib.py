@@ -45,6 +45,7 @@ les_nx, les_ny, les_nk, les_dz = 64, 64, 160, 25.0
 gcm_nlev = 91
 dtype = "f32"
 per_column = False          # True: drive the kernels through the per-LES reference-shaped calls
+gather_mode = "nccl"        # multi-GPU tendency gather: "nccl" | "p2p" | "p2p-owner" (pipeline.py)
 write_diagnostics = False
 
 gcm_model = None
@@ -84,8 +85,22 @@ def initialize(config=None, geometries=None, output_geometries=None, device=None
         grid_indices = list(range(n))
     for i in grid_indices:
         gcm_model.set_mask(i)                                                     # splib.py:121-122
+    # multi-GPU (one process per GPU under torch.distributed): every rank owns a contiguous block of
+    # the SP columns; rank 0 owns the GCM (its profiles are scattered, the tendencies gathered back)
+    world, rank = 1, 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        if len(grid_indices) % world:
+            raise ValueError("%d SP columns do not divide over %d ranks" % (len(grid_indices), world))
+    all_grid_indices = grid_indices
+    from .pipeline import shard_columns
+    lo, hi = shard_columns(len(all_grid_indices), world, rank)
+    grid_indices = all_grid_indices[lo:hi]
     les_batch = gpu_les_batch(len(grid_indices), gcm_nlev, les_nx, les_ny, les_nk, les_dz, tdt, device,
-                              couple_surface=cplsurf)
+                              col0=lo, couple_surface=cplsurf, gather=gather_mode,
+                              ncol_total=len(all_grid_indices))
+    les_batch.all_grid_indices = all_grid_indices
+    les_batch.is_gcm_owner = (rank == 0)
     les_models = les_batch.models
     for les, gi in zip(les_models, grid_indices):                                 # splib.py:146-154
         les.grid_index = gi
@@ -95,13 +110,21 @@ def initialize(config=None, geometries=None, output_geometries=None, device=None
     gcm_model.evolve_model_until_cloud_scheme()                                   # splib.py:186-188
     gcm_model.evolve_model_cloud_scheme()
     gcm_model.first_half_step_done = True
-    spcpl.gather_gcm_data(gcm_model, les_models, True)                            # splib.py:196
+    _gather(True)                                                                 # splib.py:196
     d = les_batch.cpl.gcm_to_les(les_batch.pipe.gcm, les_batch.pipe.zf, les_batch.pipe.zh, None, None, 1.0, 1.0,
                                  False, want_state=True)                          # convert_profiles, splib.py:202-203
     les_batch.initialize_state(d)                                                 # set_les_state,    splib.py:204
     les_batch.aux["PS"].copy_(d["ps"])
     firststep, profiles, timing_rows = True, {}, []
     return les_models
+
+
+def _gather(couple_surface):
+    """spcpl.gather_gcm_data on one GPU; scatter from the GCM-owning rank when the columns are sharded."""
+    if les_batch.pipe.world > 1:
+        spcpl.gather_gcm_data_sharded(gcm_model, les_batch, couple_surface)
+    else:
+        spcpl.gather_gcm_data(gcm_model, les_models, couple_surface, None, write=write_diagnostics)
 
 
 def step_les_models(model_time):
@@ -136,7 +159,7 @@ def step():
         spio.update_time(t + delta_t)
 
     gather = -time.time()
-    spcpl.gather_gcm_data(gcm_model, les_models, cplsurf, None, write=write_diagnostics)   # splib.py:312
+    _gather(cplsurf)                                                              # splib.py:312
     gather += time.time()
 
     forc = -time.time()

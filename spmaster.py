@@ -35,15 +35,37 @@ def main(argv=None):
                    help="drive the kernels through the per-LES reference-shaped calls")
     p.add_argument("--output", dest="output_name", default="spifs.npz")
     p.add_argument("--write", dest="write_diagnostics", action="store_true")
+    p.add_argument("--gather", dest="gather_mode", default="nccl", choices=["nccl", "p2p", "p2p-owner"],
+                   help="multi-GPU tendency gather (under torch.distributed.run)")
+    p.add_argument("--save_state", default=None, help="write the final GCM state of the SP columns to this .npz")
     args = p.parse_args(argv)
 
+    import os
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:   # one process per GPU: columns are sharded, rank 0 owns the GCM
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+
     from sp_coupler_b200 import splib
-    splib.initialize(args.__dict__)
-    splib.open_timing_file()
+    cfg = {k: v for k, v in args.__dict__.items() if k != "save_state"}
+    splib.initialize(cfg)
+    if rank == 0:
+        splib.open_timing_file()
     splib.run(args.gcm_steps)
     splib.finalize()
+    if args.save_state and rank == 0:
+        import numpy as np
+        cols = splib.les_batch.all_grid_indices
+        np.savez(args.save_state, **{k: splib.gcm_model.state[k][cols] for k in ("T", "SH", "QL", "QI", "U", "V", "A")})
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     rows = splib.timing_rows
-    if rows:
+    if rows and rank == 0:
         n = len(splib.les_models)
         f = sum(r[3] for r in rows[1:]) / max(len(rows) - 1, 1)
         t = sum(r[4] for r in rows[1:]) / max(len(rows) - 1, 1)

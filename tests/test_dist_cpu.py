@@ -61,3 +61,34 @@ def test_sharded_gather_equals_unsharded(tmp_path):
     # data of a column depends only on its global index
     _, v1 = _tendencies(3, 3)
     assert all(np.array_equal(v1[f], vols[f][3:]) for f in vols)
+
+
+def _scatter_worker(rank, world, port, outdir):
+    from sp_coupler_b200.pipeline import GcmScatter, GcmStaging
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ncol = NCOL // world
+    st = GcmStaging(ncol, NLEV, torch.float64, "cpu", pin=False)
+    sc = GcmScatter(st, world, rank, owner=0, device="cpu", pin=False)
+    if rank == 0:
+        sc.fill_host(synth.make_gcm_columns(NCOL, NLEV, seed=5))
+    dev = sc.scatter()
+    np.savez(os.path.join(outdir, "rank%d.npz" % rank), **{k: v.numpy() for k, v in dev.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gcm_scatter_delivers_each_ranks_columns(tmp_path):
+    """Multi-GPU gather_gcm_data: the GCM-owning rank packs per-rank blocks, one scatter delivers them."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_scatter_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    full = synth.make_gcm_columns(NCOL, NLEV, seed=5)
+    for rank in range(2):
+        got = np.load(str(tmp_path / ("rank%d.npz" % rank)))
+        lo, hi = shard_columns(NCOL, 2, rank)
+        for k in full:
+            assert np.array_equal(got[k], full[k][lo:hi]), (rank, k)
