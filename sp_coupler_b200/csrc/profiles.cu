@@ -13,6 +13,7 @@ namespace {
 using namespace spc;
 
 constexpr int kThreads = 256;
+int g_k2_threads = kThreads, g_k3_threads = kThreads;  // tuning hook (spc_tune_profiles)
 constexpr double kC = rv / rd - 1;          // spcpl.py:175
 constexpr double kExp = rd / cp;            // sputils.py:29
 constexpr double kIExp = -rd / cp;          // sputils.py:34
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(kThreads) gcm_to_les_kernel(const K2Args a) {
   const double zs = ld<T>(a.g.Zghalf, bh + nlev);   // Zghalf[-1]
   const spc_les_forcing& o = a.o;
 
-  for (int l = threadIdx.x; l <= nlev; l += kThreads) {
+  for (int l = threadIdx.x; l <= nlev; l += blockDim.x) {
     const double Zh = (ld<T>(a.g.Zghalf, bh + l) - zs) / grav;          // spcpl.py:197
     st<T>(o.Zh, bh + l, Zh);
     if (l < nlev && o.slab_idx && a.zh) {
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kThreads) gcm_to_les_kernel(const K2Args a) {
   __syncthreads();
 
   const size_t pf = (size_t)ncol * nk;   // field stride of les_prof [5][ncol][nk]
-  for (int k = threadIdx.x; k < nk; k += kThreads) {
+  for (int k = threadIdx.x; k < nk; k += blockDim.x) {
     const double x = __ldg(a.zf + k);
     const int j = upper_bound(Zf, nlev, x) - 1;
     const size_t i = (size_t)c * nk + k;
@@ -322,15 +323,15 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
   const spc_gcm_tend& o = a.o;
   const size_t pfs = (size_t)ncol * nk;
 
-  for (int l = threadIdx.x; l < nlev; l += kThreads) {
+  for (int l = threadIdx.x; l < nlev; l += blockDim.x) {
     ZfA[nlev - 1 - l] = (ld<T>(a.g.Zgfull, b + l) - zs) / grav;         // les.gcm_Zf, spcpl.py:198,390
     PfA[nlev - 1 - l] = ld<T>(a.g.Pfull, b + l);
   }
   // projected cloud counts were written to o.cntslab by the projection kernel launched just before
   const bool from_mask = (a.les.A == nullptr) && a.les.mask && o.cntslab;
   if (a.conservative)
-    for (int l = threadIdx.x; l <= nlev; l += kThreads) ZhD[l] = (ld<T>(a.g.Zghalf, bh + l) - zs) / grav;
-  for (int k = threadIdx.x; k < nk; k += kThreads) {
+    for (int l = threadIdx.x; l <= nlev; l += blockDim.x) ZhD[l] = (ld<T>(a.g.Zghalf, bh + l) - zs) / grav;
+  for (int k = threadIdx.x; k < nk; k += blockDim.x) {
     const size_t i = (size_t)c * nk + k;
     zf[k] = __ldg(a.zf + k);
     const double ql = __ldg(a.les.prof + SPC_QL * pfs + i);
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
 
   // diagnostic temperature on LES levels, spcpl.py:408-409
   if (o.t || o.bracket_pf) {
-    for (int k = threadIdx.x; k < nk; k += kThreads) {
+    for (int k = threadIdx.x; k < nk; k += blockDim.x) {
       const size_t i = (size_t)c * nk + k;
       const int j = upper_bound(ZfA, nlev, zf[k]) - 1;
       if (o.bracket_pf) o.bracket_pf[i] = j;
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
 
   const double npts = (double)a.les.nx * (double)a.les.ny;
   const double zh_top = a.zh ? __ldg(a.zh + nk - 1) : 0.0;
-  for (int l = threadIdx.x; l < nlev; l += kThreads) {
+  for (int l = threadIdx.x; l < nlev; l += blockDim.x) {
     const size_t i = b + l;
     const int r = nlev - 1 - l;                  // ascending slab index of GCM level l
     double A_d;                                  // profile["A"][::-1], spcpl.py:404
@@ -481,6 +482,13 @@ int check_gcm(const spc_gcm_cols* g, int couple_surface, const char* who) {
 
 extern "C" {
 
+// Tuning hook, not part of the public ABI (tools/step_probe.py only): threads per column CTA of K2 / K3.
+int spc_tune_profiles(int k2_threads, int k3_threads) {
+  if (k2_threads >= 32 && k2_threads <= kThreads) g_k2_threads = k2_threads & ~31;
+  if (k3_threads >= 32 && k3_threads <= kThreads) g_k3_threads = k3_threads & ~31;
+  return SPC_OK;
+}
+
 int spc_gcm_to_les(spc_handle h, const spc_gcm_cols* gcm, const double* zf, const double* zh, int nk,
                    const double* les_prof, const void* ps_les, double dt, double factor, int couple_surface,
                    const spc_les_forcing* out, void* stream) {
@@ -504,8 +512,8 @@ int spc_gcm_to_les(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   a.o = *out;
   a.dt = dt; a.factor = factor; a.nk = nk; a.couple_surface = couple_surface;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (gcm->dtype == SPC_F32) gcm_to_les_kernel<float><<<gcm->ncol, kThreads, smem, st>>>(a);
-  else gcm_to_les_kernel<double><<<gcm->ncol, kThreads, smem, st>>>(a);
+  if (gcm->dtype == SPC_F32) gcm_to_les_kernel<float><<<gcm->ncol, g_k2_threads, smem, st>>>(a);
+  else gcm_to_les_kernel<double><<<gcm->ncol, g_k2_threads, smem, st>>>(a);
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
 }
@@ -551,8 +559,8 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   a.n_peers = out->tend_peers ? out->n_peers : 0;
   for (int p = 0; p < a.n_peers; ++p) a.peers[p] = out->tend_peers[p];
   a.peer_off = (size_t)out->peer_col0 * SPC_NTEND * gcm->nlev;
-  if (gcm->dtype == SPC_F32) les_to_gcm_kernel<float><<<gcm->ncol, kThreads, smem, st>>>(a);
-  else les_to_gcm_kernel<double><<<gcm->ncol, kThreads, smem, st>>>(a);
+  if (gcm->dtype == SPC_F32) les_to_gcm_kernel<float><<<gcm->ncol, g_k3_threads, smem, st>>>(a);
+  else les_to_gcm_kernel<double><<<gcm->ncol, g_k3_threads, smem, st>>>(a);
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
 }

@@ -9,6 +9,8 @@
 // complete_tx). Lane 0 keeps the ring full; the warp reduces a landed chunk in 4 KB sub-blocks with
 // conflict-free 128-bit LDS, accumulating in float64 (so the mean is order-insensitive to ~1e-16),
 // and finishes a slab with a shuffle butterfly. No block-wide barriers, no atomics, fixed order.
+#include <type_traits>
+
 #include "spc_common.cuh"
 
 namespace {
@@ -388,6 +390,294 @@ __global__ void __launch_bounds__(1024) slab_reduce_ijk_kernel(const K1Args a, i
   }
 }
 
+// IJK fast path: per-warp TMA rings over the contiguous [S][nk] block of one (field, column) item.
+// A 16-byte vector v of the block holds levels (v % nkv)*VEC .. +VEC-1, so with a period of
+// P = lcm(nkv, 32) vectors lane `l` sees the same level group in slot `it` of every period:
+// (it*32 + l) % nkv. Each lane therefore keeps SLOTS x VEC float64 partial sums in registers and never
+// needs to know which horizontal point it is looking at. Persistent CTAs own whole items; the chunks of
+// a CTA's items form one sequence that is dealt round-robin to its warps, so the rings never drain at an
+// item boundary. When a warp has finished its share of an item it parks its partials in shared memory
+// and carries on with the next item; once all warps have parked, each warp combines its slice of the
+// levels in a fixed order (bit-reproducible, no atomics on data) the next time it looks. No block-wide
+// barrier in the steady state. Items are numbered column-major (item = c*5 + f) so that at any moment the
+// SMs are spread over all five fields and the heavier ql items (count + mask) overlap with the others.
+template <int WARPS_, int CHUNK_, int BATCH5_ = 2>
+struct IjkRing {
+  static constexpr int kWarps = WARPS_, kChunk = CHUNK_, kBatch5 = BATCH5_;  // kBatch5: periods per pass when SLOTS >= 4
+};
+
+struct IjkArgs {
+  int nk, ncol, nkv;          // levels, columns, 16-byte vectors per horizontal point
+  int chunk_bytes;            // whole periods per TMA chunk, <= kChunk
+  int nch;                    // chunks per item
+  long long item_bytes;       // S*nk*sizeof(T)
+  long long nitems;           // 5*ncol
+  int want_mask;
+};
+
+// UU periods of a landed chunk: all 128-bit LDS are issued before the first conversion.
+template <typename T, int SLOTS, int UU, bool QL, bool MASK>
+__device__ __forceinline__ void ijk_periods(const uint8_t* pb, int lane, double thr, uint32_t* mw,
+                                            double (&acc)[SLOTS][16 / sizeof(T)], int (&cnt)[SLOTS][16 / sizeof(T)]) {
+  constexpr int VEC = 16 / (int)sizeof(T), LPW = 32 / VEC, P = SLOTS * 32;
+  if constexpr (sizeof(T) == 4) {
+    float4 v[UU][SLOTS];
+#pragma unroll
+    for (int u = 0; u < UU; ++u)
+#pragma unroll
+      for (int it = 0; it < SLOTS; ++it) v[u][it] = reinterpret_cast<const float4*>(pb)[u * P + it * 32 + lane];
+#pragma unroll
+    for (int u = 0; u < UU; ++u)
+#pragma unroll
+      for (int it = 0; it < SLOTS; ++it) {
+        const double d0 = (double)v[u][it].x, d1 = (double)v[u][it].y, d2 = (double)v[u][it].z, d3 = (double)v[u][it].w;
+        acc[it][0] += d0;
+        acc[it][1] += d1;
+        acc[it][2] += d2;
+        acc[it][3] += d3;
+        if constexpr (QL) {
+          const uint32_t b0 = d0 > thr, b1 = d1 > thr, b2 = d2 > thr, b3 = d3 > thr;
+          cnt[it][0] += b0;
+          cnt[it][1] += b1;
+          cnt[it][2] += b2;
+          cnt[it][3] += b3;
+          if constexpr (MASK) {
+            uint32_t word = (b0 | (b1 << 1) | (b2 << 2) | (b3 << 3)) << (4 * (lane & 7));
+            word |= __shfl_xor_sync(kFull, word, 1);  // (redux.sync.or over the 8-lane group measured 16 % slower)
+            word |= __shfl_xor_sync(kFull, word, 2);
+            word |= __shfl_xor_sync(kFull, word, 4);
+            if ((lane & 7) == 0) mw[(u * P + it * 32) / LPW] = word;
+          }
+        }
+      }
+  } else {
+    double2 v[UU][SLOTS];
+#pragma unroll
+    for (int u = 0; u < UU; ++u)
+#pragma unroll
+      for (int it = 0; it < SLOTS; ++it) v[u][it] = reinterpret_cast<const double2*>(pb)[u * P + it * 32 + lane];
+#pragma unroll
+    for (int u = 0; u < UU; ++u)
+#pragma unroll
+      for (int it = 0; it < SLOTS; ++it) {
+        acc[it][0] += v[u][it].x;
+        acc[it][1] += v[u][it].y;
+        if constexpr (QL) {
+          const uint32_t b0 = v[u][it].x > thr, b1 = v[u][it].y > thr;
+          cnt[it][0] += b0;
+          cnt[it][1] += b1;
+          if constexpr (MASK) {
+            uint32_t word = (b0 | (b1 << 1)) << (2 * (lane & 15));
+            word |= __shfl_xor_sync(kFull, word, 1);
+            word |= __shfl_xor_sync(kFull, word, 2);
+            word |= __shfl_xor_sync(kFull, word, 4);
+            word |= __shfl_xor_sync(kFull, word, 8);
+            if ((lane & 15) == 0) mw[(u * P + it * 32) / LPW] = word;
+          }
+        }
+      }
+  }
+}
+
+template <typename T, int SLOTS, int BATCH5, bool QL, bool MASK>
+__device__ __forceinline__ void ijk_chunk(const uint8_t* buf, int nper, int lane, double thr, uint32_t* mw,
+                                          double (&acc)[SLOTS][16 / sizeof(T)], int (&cnt)[SLOTS][16 / sizeof(T)]) {
+  constexpr int VEC = 16 / (int)sizeof(T), LPW = 32 / VEC, P = SLOTS * 32;
+  constexpr int kBatch = SLOTS >= 4 ? BATCH5 : 8 / SLOTS;
+  int p = 0;
+#pragma unroll 1
+  for (; p + kBatch <= nper; p += kBatch)
+    ijk_periods<T, SLOTS, kBatch, QL, MASK>(buf + (size_t)p * (P * 16), lane, thr, MASK ? mw + (p * P) / LPW : nullptr, acc, cnt);
+#pragma unroll 1
+  for (; p < nper; ++p)
+    ijk_periods<T, SLOTS, 1, QL, MASK>(buf + (size_t)p * (P * 16), lane, thr, MASK ? mw + (p * P) / LPW : nullptr, acc, cnt);
+}
+
+template <typename T, int SLOTS, typename R>
+__global__ void __launch_bounds__(R::kWarps * 32, 1) slab_reduce_ijk_tma_kernel(const K1Args a, const IjkArgs g) {
+  constexpr int kWarps = R::kWarps, kChunk = R::kChunk;
+  constexpr int VEC = 16 / (int)sizeof(T);     // levels per vector
+  constexpr int LPW = 32 / VEC;                // lanes that share one 32-level mask word
+  constexpr int P = SLOTS * 32;                // vectors per period
+  extern __shared__ __align__(128) uint8_t smem[];
+  // [kWarps][kChunk] ring | [kWarps][P][VEC] double partial sums | [kWarps][P][VEC] int partial counts | mbarriers | flags
+  double* psum = reinterpret_cast<double*>(smem + (size_t)kWarps * kChunk);
+  int* pcnt = reinterpret_cast<int*>(psum + (size_t)kWarps * P * VEC);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pcnt + (size_t)kWarps * P * VEC);
+  unsigned int* sync = reinterpret_cast<unsigned int*>(bars + kWarps);   // [0] partials parked, [1] level slices combined
+  volatile unsigned int* vsync = sync;
+  // the shuffle tells the compiler that the warp index is warp-uniform, so every branch below that depends on the
+  // warp's item / chunk cursor is uniform too and the mask shuffles need no re-convergence wrappers
+  const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  uint8_t* wbuf = smem + (size_t)warp * kChunk;
+  const uint32_t wbuf_s = smem_u32(wbuf);
+  const uint32_t bar = smem_u32(bars + warp);
+
+  if (threadIdx.x == 0) {
+    sync[0] = 0u;
+    sync[1] = 0u;
+  }
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // items of this CTA: blockIdx.x + io*gridDim.x; its chunk sequence Q = io*nch + j; warp w takes Q = w (mod kWarps).
+  // (io, j) are carried incrementally: no 64-bit division on the per-chunk path.
+  const int my_items = blockIdx.x < g.nitems ? (int)((g.nitems - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  if (my_items == 0) return;
+  const uint64_t pol = l2_evict_first_policy();
+  const int nch_mod = g.nch % kWarps;
+
+  int pio = 0, pj = warp;  // producer cursor (lane 0): next chunk of this warp to fetch
+  while (pj >= g.nch && pio < my_items) {
+    pj -= g.nch;
+    ++pio;
+  }
+  auto issue = [&]() {
+    const unsigned int item = blockIdx.x + (unsigned int)pio * gridDim.x;
+    const unsigned int c = item / SPC_NFIELDS;
+    const int f = (int)(item - c * SPC_NFIELDS);
+    const uint8_t* src = static_cast<const uint8_t*>(field_ptr(a, f)) + (size_t)c * g.item_bytes + (size_t)pj * g.chunk_bytes;
+    const uint32_t bytes = (uint32_t)min((long long)g.chunk_bytes, g.item_bytes - (long long)pj * g.chunk_bytes);
+    mbar_arrive_expect_tx(bar, bytes);
+    tma_bulk_g2s(wbuf_s, src, bytes, bar, pol);
+    pj += kWarps;
+    while (pj >= g.nch && pio < my_items) {
+      pj -= g.nch;
+      ++pio;
+    }
+  };
+  if (lane == 0 && pio < my_items) issue();
+
+  double acc[SLOTS][VEC];
+  int cnt[SLOTS][VEC];
+#pragma unroll
+  for (int it = 0; it < SLOTS; ++it)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      acc[it][c] = 0.0;
+      cnt[it][c] = 0;
+    }
+
+  // Combines this warp's slice of the levels of item ordinal `pending` once every warp has parked its partials
+  // (must = wait for that). Two lanes per level: lane halves sum the chunk classes [0, kWarps/2) and
+  // [kWarps/2, kWarps) in order (within a class the period vectors of the level group), then lower + upper.
+  int pending = -1;
+  const int k_lo = (int)((long long)warp * g.nk / kWarps), k_hi = (int)((long long)(warp + 1) * g.nk / kWarps);
+  auto combine = [&](bool must) {
+    if (pending < 0) return;
+    const unsigned int need = (unsigned int)kWarps * (unsigned int)(pending + 1);
+    unsigned int have = 0;
+    if (lane == 0) {
+      have = vsync[0];
+      while (must && have < need) have = vsync[0];
+    }
+    have = __shfl_sync(kFull, have, 0);
+    if (have < need) return;
+    __threadfence_block();
+    const unsigned int item = blockIdx.x + (unsigned int)pending * gridDim.x;
+    const unsigned int c = item / SPC_NFIELDS;
+    const int f = (int)(item - c * SPC_NFIELDS);
+    const bool is_ql = (f == SPC_QL) && a.cnt != nullptr;
+    const int dup = P / g.nkv;  // period vectors holding the same level group
+    const int half = lane >> 4, w0 = half * (kWarps / 2), w1 = half ? kWarps : kWarps / 2;
+    for (int kb = k_lo; kb < k_hi; kb += 16) {       // warp-uniform trip count
+      const int k = kb + (lane & 15);
+      const bool live = k < k_hi;
+      const int kg = k / VEC, cc = k - kg * VEC;
+      double s = 0.0;
+      int n = 0;
+      if (live) {
+        for (int w = w0; w < w1; ++w) {
+          double t = 0.0;
+          for (int d = 0; d < dup; ++d) {
+            const size_t e = ((size_t)w * P + kg + (size_t)d * g.nkv) * VEC + cc;
+            t += psum[e];
+            if (is_ql) n += pcnt[e];
+          }
+          s += t;
+        }
+      }
+      const double s_hi = __shfl_down_sync(kFull, s, 16);
+      const int n_hi = __shfl_down_sync(kFull, n, 16);
+      if (live && half == 0) {
+        a.prof[((size_t)f * g.ncol + c) * g.nk + k] = (s + s_hi) / (double)a.S;
+        if (is_ql) a.cnt[(size_t)c * g.nk + k] = n + n_hi;
+      }
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&sync[1], 1u);
+    pending = -1;
+  };
+
+  // parks this warp's partials of item ordinal `io` under chunk class `cls`
+  auto flush = [&](int io, int cls) {
+    combine(true);                                                  // my slice of the previous item
+    if (lane == 0)
+      while (vsync[1] < (unsigned int)kWarps * (unsigned int)io) {  // every slice of it: the parking area is free
+      }
+    __syncwarp();
+    double* ps = psum + ((size_t)cls * P) * VEC;
+    int* pc = pcnt + ((size_t)cls * P) * VEC;
+#pragma unroll
+    for (int it = 0; it < SLOTS; ++it)
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        ps[(size_t)(it * 32 + lane) * VEC + c] = acc[it][c];
+        pc[(size_t)(it * 32 + lane) * VEC + c] = cnt[it][c];
+        acc[it][c] = 0.0;
+        cnt[it][c] = 0;
+      }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&sync[0], 1u);
+    pending = io;
+  };
+
+  uint32_t parity = 0;
+  // consumer cursor: chunk j of item ordinal io; cls = the chunk class (j % kWarps) this warp serves in item io -
+  // a rotation of the warp index, so the combine order, hence every bit of the result, does not depend on where
+  // the item sits in the batch
+  int io = 0, j = warp, cls = warp;
+  for (;;) {
+    while (j >= g.nch && io < my_items) {  // this warp is done with item io
+      flush(io, cls);
+      j -= g.nch;
+      ++io;
+      cls = (cls - nch_mod + kWarps) % kWarps;
+    }
+    if (io >= my_items) break;
+    combine(false);
+    const unsigned int item = blockIdx.x + (unsigned int)io * gridDim.x;
+    const unsigned int c = item / SPC_NFIELDS;
+    const int f = (int)(item - c * SPC_NFIELDS);
+    const bool is_ql = (f == SPC_QL) && (a.cnt != nullptr || a.mask != nullptr);
+    const bool do_mask = (f == SPC_QL) && g.want_mask;
+    const int bytes = (int)min((long long)g.chunk_bytes, g.item_bytes - (long long)j * g.chunk_bytes);
+    const int nper = bytes / (P * 16);
+    while (!mbar_try_wait(bar, parity)) {
+    }
+    parity ^= 1;
+    if (do_mask) {
+      // mask word of vector v of the item: v / LPW (nk % 32 == 0 on this path when the mask is wanted)
+      uint32_t* mw = a.mask + (size_t)c * ((size_t)a.S * (g.nk >> 5)) + ((size_t)j * (g.chunk_bytes >> 4)) / LPW + lane / LPW;
+      ijk_chunk<T, SLOTS, R::kBatch5, true, true>(wbuf, nper, lane, a.thr, mw, acc, cnt);
+    } else if (is_ql) {
+      ijk_chunk<T, SLOTS, R::kBatch5, true, false>(wbuf, nper, lane, a.thr, nullptr, acc, cnt);
+    } else {
+      ijk_chunk<T, SLOTS, R::kBatch5, false, false>(wbuf, nper, lane, a.thr, nullptr, acc, cnt);
+    }
+    __syncwarp();  // every lane is done with the stage before it is refilled
+    if (lane == 0 && pio < my_items) issue();
+    j += kWarps;
+  }
+  combine(true);
+}
+
 bool fast_path(int dtype, long long S) {
   const long long slab_bytes = S * (dtype == SPC_F32 ? 4 : 8);
   return slab_bytes % 16 == 0 && slab_bytes >= 1024;
@@ -450,9 +740,72 @@ int launch_kji(spc_handle h, const K1Args& a, bool fast, cudaStream_t st) {
   return SPC_OK;
 }
 
+int g_ijk_variant = 0;  // tuning hook (spc_tune_k1 with 100 + id): 0 = TMA path when eligible, 1 = always the CTA-per-item kernel
+
+template <typename T, int SLOTS, typename R>
+int launch_ijk_tma(spc_handle h, const K1Args& a, IjkArgs g, cudaStream_t st) {
+  constexpr int VEC = 16 / (int)sizeof(T), P = SLOTS * 32;
+  static_assert(P * 16 <= R::kChunk, "a period must fit one ring stage");
+  g.chunk_bytes = (R::kChunk / (P * 16)) * (P * 16);
+  g.nch = (int)((g.item_bytes + g.chunk_bytes - 1) / g.chunk_bytes);
+  const size_t smem = (size_t)R::kWarps * R::kChunk + (size_t)R::kWarps * P * VEC * (sizeof(double) + sizeof(int)) +
+                      (size_t)R::kWarps * 8 + 16;
+  static thread_local int configured_dev = -1;
+  if (configured_dev != h->device) {
+    SPC_CUDA(cudaFuncSetAttribute(slab_reduce_ijk_tma_kernel<T, SLOTS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_dev = h->device;
+  }
+  const int grid = (int)std::min<long long>(h->num_sms, g.nitems);
+  slab_reduce_ijk_tma_kernel<T, SLOTS, R><<<grid, R::kWarps * 32, smem, st>>>(a, g);
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+template <typename T, int SLOTS>
+int launch_ijk_tma_variant(spc_handle h, const K1Args& a, const IjkArgs& g, cudaStream_t st) {
+  switch (g_ijk_variant) {
+    case 2: return launch_ijk_tma<T, SLOTS, IjkRing<12, 8192, 1>>(h, a, g, st);
+    default: return launch_ijk_tma<T, SLOTS, IjkRing<12, 8192, 2>>(h, a, g, st);
+  }
+}
+
+// Eligibility of the IJK TMA path: whole 16-byte vectors per point, a period of at most 5 x 32 vectors,
+// whole periods per item, 16-byte aligned volumes, and (for the per-point mask) nk a multiple of 32.
+template <typename T>
+bool ijk_tma_plan(const K1Args& a, int ncol, int nk, IjkArgs& g, int& slots) {
+  constexpr int V = 16 / (int)sizeof(T);
+  if (g_ijk_variant == 1 || nk % V != 0) return false;
+  const int nkv = nk / V;
+  int gcd = nkv, b = 32;
+  while (b) { const int t = gcd % b; gcd = b; b = t; }
+  slots = nkv / gcd;
+  const int rows_per_period = 32 / gcd;
+  if (slots > 5 || a.S % rows_per_period != 0) return false;
+  if (a.mask && nk % 32 != 0) return false;
+  const void* vols[SPC_NFIELDS] = {a.v0, a.v1, a.v2, a.v3, a.v4};
+  for (int f = 0; f < SPC_NFIELDS; ++f)
+    if (reinterpret_cast<uintptr_t>(vols[f]) % 16 != 0) return false;
+  g.nk = nk; g.ncol = ncol; g.nkv = nkv;
+  g.item_bytes = (long long)a.S * nk * (long long)sizeof(T);
+  g.nitems = (long long)SPC_NFIELDS * ncol;
+  g.want_mask = a.mask != nullptr;
+  return true;
+}
+
 template <typename T>
 int launch_ijk(spc_handle h, const K1Args& a, int ncol, int nk, cudaStream_t st) {
   constexpr int V = 16 / sizeof(T);
+  IjkArgs g;
+  int slots = 0;
+  if (ijk_tma_plan<T>(a, ncol, nk, g, slots)) {
+    switch (slots) {
+      case 1: return launch_ijk_tma_variant<T, 1>(h, a, g, st);
+      case 2: return launch_ijk_tma_variant<T, 2>(h, a, g, st);
+      case 3: return launch_ijk_tma_variant<T, 3>(h, a, g, st);
+      case 4: return launch_ijk_tma_variant<T, 4>(h, a, g, st);
+      default: return launch_ijk_tma_variant<T, 5>(h, a, g, st);
+    }
+  }
   bool vec = (nk % V == 0);
   const void* vols[SPC_NFIELDS] = {a.v0, a.v1, a.v2, a.v3, a.v4};
   for (int f = 0; f < SPC_NFIELDS && vec; ++f) vec = (reinterpret_cast<uintptr_t>(vols[f]) % 16 == 0);
@@ -483,7 +836,8 @@ extern "C" {
 
 // Tuning hook, not part of the public ABI (tools/k1_probe.py only): selects the TMA ring shape.
 int spc_tune_k1(int variant) {
-  g_k1_variant = variant;
+  if (variant >= 100) g_ijk_variant = variant - 100;
+  else g_k1_variant = variant;
   return SPC_OK;
 }
 

@@ -106,3 +106,33 @@ def test_c5_shape_per_gpu(cpl, cuda_device):
 def test_c4_full_size(cpl, cuda_device):
     """512 columns, 256x256x160, L91, float32 (107 GB): slabs of 256 KB span 32 TMA chunks."""
     _run_config(cpl, cuda_device, 512, 256, 160, 91, spots=(511,), chunk=4)
+
+
+def test_ijk_layout_full_columns(cpl, cuda_device):
+    """512 columns of 64x64x160 in the k-fastest (OMUSE) layout: the TMA-ring IJK kernel gives the same
+    exact counts and projected cloud cover as the KJI kernel on the transposed volumes, means to 1e-14,
+    and identical bits on a second pass and on a column sub-range (17 items per CTA, rings never drain)."""
+    ncol, nx, nk, nlev = 512, 64, 160, 91
+    zf, zh = synth.les_grid(nk)
+    gcm = synth.make_gcm_columns(ncol, nlev, seed=45, dtype=np.float32)
+    vols = synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=45, dtype=torch.float32)
+    kji = cpl.slab_reduce(vols)
+    ijk_vols = [v.permute(0, 3, 2, 1).contiguous() for v in vols]
+    del vols
+    ijk = cpl.slab_reduce(ijk_vols, layout="ijk")
+    assert torch.equal(ijk["cnt"], kji["cnt"])
+    err = (ijk["prof"] - kji["prof"]).abs().amax(dim=(1, 2)) / kji["prof"].abs().amax(dim=(1, 2))
+    assert float(err.max()) <= 1e-14
+    d_gcm = {k: torch.from_numpy(v).to(cuda_device) for k, v in gcm.items()}
+    d_zf, d_zh = torch.from_numpy(zf).to(cuda_device), torch.from_numpy(zh).to(cuda_device)
+    ps = torch.full((ncol,), 1.0e5, dtype=torch.float32, device=cuda_device)
+    frc = cpl.gcm_to_les(d_gcm, d_zf, d_zh, kji["prof"], ps, 900.0, 1.0, True)
+    _, cs_kji = cpl.cloud_fraction(kji, frc["slab_idx"])
+    _, cs_ijk = cpl.cloud_fraction(ijk, frc["slab_idx"])
+    assert torch.equal(cs_kji, cs_ijk)
+    again = cpl.slab_reduce(ijk_vols, layout="ijk")
+    for k in ("prof", "cnt", "mask"):
+        assert torch.equal(again[k], ijk[k]), k
+    part = cpl.slab_reduce([v[100:131] for v in ijk_vols], layout="ijk")
+    assert torch.equal(part["prof"], ijk["prof"][:, 100:131]) and torch.equal(part["cnt"], ijk["cnt"][100:131])
+    assert torch.equal(part["mask"], ijk["mask"][100:131])

@@ -94,6 +94,42 @@ def test_ijk_layout_matches_oracle(cpl, cuda_device, dtype, shape):
     assert np.array_equal(n(slab2["cnt"]), ref["cnt"])
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [
+    (40, 8, 8, 160, 19),     # 200 items > 148 CTAs: several items per CTA; 6 chunks per item < 12 warps
+    (3, 16, 16, 128, 19),    # one slot per lane (float32), two (float64)
+    (3, 16, 16, 96, 19),     # three-slot period
+    (2, 16, 16, 64, 19),     # two horizontal points per period
+    (2, 8, 8, 256, 19),      # two / four slots
+    (2, 64, 64, 160, 91),    # C3 column shape
+    (1, 4, 1, 160, 19),      # a single period per item: eleven warps have nothing to do
+])
+def test_ijk_tma_path_matches_oracle(cpl, cuda_device, dtype, shape):
+    """IJK shapes that take the per-warp TMA ring kernel (whole 16-byte vectors per point, period of at most
+    5 x 32 vectors, nk % 32 == 0 for the mask): means, counts, per-point mask -> projected cloud cover, and the
+    same bits from the CTA-per-item kernel it replaces."""
+    import torch
+    from sp_coupler_b200 import _abi
+    ncol, nx, ny, nk, nlev = shape
+    case = cases.host_case(ncol, nx, ny, nk, nlev, dtype, layout=1, dz=25.0)
+    ref = cases.oracle_step(case)
+    d = cases.to_device(case, cuda_device)
+    slab, frc, tnd = cases.gpu_step(cpl, d, layout=1)
+    check_step(case, ref, slab, frc, tnd, RTOL[dtype])
+    A, cs = cpl.cloud_fraction(slab, frc["slab_idx"])
+    assert np.array_equal(n(cs), ref["cntslab"])
+    try:
+        _abi.lib().spc_tune_k1(101)            # force the older CTA-per-item kernel
+        old = cpl.slab_reduce(d["vols"], layout="ijk", want_mask=True)
+    finally:
+        _abi.lib().spc_tune_k1(100)
+    assert torch.equal(old["cnt"], slab["cnt"]) and torch.equal(old["mask"], slab["mask"])
+    assert relerr(n(old["prof"]), n(slab["prof"])) <= 1e-14
+    again = cpl.slab_reduce(d["vols"], layout="ijk", want_mask=True)
+    for k in ("prof", "cnt", "mask"):
+        assert torch.equal(again[k], slab[k]), k   # fixed summation order: bit-reproducible
+
+
 @pytest.mark.parametrize("thr", [-1.0, 0.0, 1e-5])
 def test_cloud_threshold_semantics(cpl, cuda_device, thr):
     """strict '>' on the float64 value; a negative threshold must not count chunk padding."""
@@ -105,6 +141,30 @@ def test_cloud_threshold_semantics(cpl, cuda_device, thr):
     assert np.array_equal(n(tnd["cntslab"]), ref["cntslab"])
     if thr < 0:
         assert (ref["cnt"] == 1600).all()
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("thr", [1e-5, 2.5e-4, float(np.float32(1e-5)), -3e-7])
+def test_cloud_threshold_at_float32_neighbours(cpl, cuda_device, thr, layout):
+    """float32 volumes are compared in float32 against the largest float32 <= thr; that must count exactly the
+    cells with float64(ql) > thr, also when ql sits on the float32 values right around the threshold."""
+    import torch
+    rng = np.random.default_rng(7)
+    ncol, nx, ny, nk = 2, 32, 32, 32
+    t32 = np.float32(thr)
+    cand = np.array([t32, np.nextafter(t32, np.float32(-np.inf)), np.nextafter(t32, np.float32(np.inf)),
+                     np.float32(0.0), np.float32(2 * abs(thr))], dtype=np.float32)
+    ql = cand[rng.integers(0, len(cand), size=(ncol, nk, ny, nx))]
+    expect = np.count_nonzero(ql.astype(np.float64) > thr, axis=(2, 3)).astype(np.int32)
+    vols = [torch.zeros((ncol, nk, ny, nx), dtype=torch.float32, device=cuda_device) for _ in range(5)]
+    vols[2] = torch.from_numpy(ql).to(cuda_device)
+    if layout == 1:
+        vols = [v.permute(0, 3, 2, 1).contiguous() for v in vols]
+    slab = cpl.slab_reduce(vols, layout="kji" if layout == 0 else "ijk", ql_thresh=thr)
+    assert np.array_equal(n(slab["cnt"]), expect)
+    idx = torch.full((ncol, 4), nk, dtype=torch.int32, device=cuda_device)      # one slab holding every level
+    _, cs = cpl.cloud_fraction(slab, idx)
+    assert np.array_equal(n(cs)[:, 0], np.count_nonzero((ql.astype(np.float64) > thr).any(axis=1), axis=(1, 2)))
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)

@@ -20,7 +20,11 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--layout", default="kji")
 ap.add_argument("--nomask", action="store_true")
 ap.add_argument("--variants", default="0", help="comma list of spc_tune_k1 ring variants to time")
+ap.add_argument("--lib", default="", help="alternative libspcpl_b200 build to time (A/B on the same box)")
 a = ap.parse_args()
+if a.lib:
+    from sp_coupler_b200 import _abi as _abi0
+    _abi0.LIB_PATH = os.path.abspath(a.lib)
 dev = torch.device("cuda:0")
 cpl = Coupler(dev)
 td = torch.float32 if a.dtype == "f32" else torch.float64
@@ -52,6 +56,7 @@ for variant in [int(x) for x in a.variants.split(",")]:
           % (variant, a.layout, a.ncol, a.nx, a.nx, a.nk, a.dtype, not a.nomask, np.median(ts), ts.min(),
              nbytes / np.median(ts) / 1e6, nbytes / ts.min() / 1e6, a.ncol / np.median(ts) * 1e3))
 _abi.lib().spc_tune_k1(0)
+_abi.lib().spc_tune_k1(100)
 # set_les_state write bandwidth
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 prof = torch.zeros((a.ncol, a.nk), dtype=torch.float64, device=dev)
