@@ -13,7 +13,15 @@ namespace {
 using namespace spc;
 
 constexpr int kThreads = 256;
-int g_k2_threads = kThreads, g_k3_threads = kThreads;  // tuning hook (spc_tune_profiles)
+int g_k2_threads = 0, g_k3_threads = 0;  // tuning hook (spc_tune_profiles); 0 = from the shape
+int g_proj_threads = 0;                  // threads of the cloud projection CTA; 0 = by mask row size (64 up to 512 B per level, else 256)
+
+// Threads per column CTA: one per level of the longer of the two profiles, whole warps, at most kThreads.
+// (256 threads for 137 / 160 levels left three of eight warps idle and capped the resident useful warps.)
+int column_threads(int tuned, int n) {
+  if (tuned) return tuned;
+  return std::min(kThreads, std::max(32, (n + 31) & ~31));
+}
 constexpr double kC = rv / rd - 1;          // spcpl.py:175
 constexpr double kExp = rd / cp;            // sputils.py:29
 constexpr double kIExp = -rd / cp;          // sputils.py:34
@@ -64,16 +72,22 @@ __global__ void __launch_bounds__(kThreads) gcm_to_les_kernel(const K2Args a) {
   double* ql = qt + nlev;
   double* u = ql + nlev;
   double* v = u + nlev;
+  double* zh_s = v + nlev;       // [nk] LES half levels (only when the cloud-slab mapping is wanted)
   const size_t b = (size_t)c * nlev, bh = (size_t)c * (nlev + 1);
   const double zs = ld<T>(a.g.Zghalf, bh + nlev);   // Zghalf[-1]
   const spc_les_forcing& o = a.o;
+  const bool want_idx = o.slab_idx && a.zh;         // block-uniform
+  if (want_idx) {
+    for (int k = threadIdx.x; k < nk; k += blockDim.x) zh_s[k] = __ldg(a.zh + k);
+    __syncthreads();
+  }
 
   for (int l = threadIdx.x; l <= nlev; l += blockDim.x) {
     const double Zh = (ld<T>(a.g.Zghalf, bh + l) - zs) / grav;          // spcpl.py:197
     st<T>(o.Zh, bh + l, Zh);
-    if (l < nlev && o.slab_idx && a.zh) {
+    if (l < nlev && want_idx) {
       // searchsorted(zh, Zh, side="right")[:-1][::-1]  (spcpl.py:26,764)
-      o.slab_idx[b + (nlev - 1 - l)] = upper_bound(a.zh, nk, Zh);
+      o.slab_idx[b + (nlev - 1 - l)] = upper_bound(zh_s, nk, Zh);
     }
     if (l == nlev) break;
     const double Tl = ld<T>(a.g.T, b + l), SH = ld<T>(a.g.SH, b + l);
@@ -173,59 +187,117 @@ __device__ double integral_w(double a, double b, const double* z, int n, const d
 // ---- projected cloud cover per GCM slab (les.get_cloudfraction(indices), spcpl.py:28,765) ----------
 // Slab r of a column covers the LES levels [k0, k1), k1 = min(max(idx[0..r]), nk), k0 likewise for r-1
 // (idx = searchsorted(zh, Zh, 'right')[:-1][::-1], spcpl.py:26,764, made monotone and clipped).
-// KJI mask: one block per column, ONE WARP per slab. The mask layout is opaque but identical for every
-// level, so the warp ORs the slab's levels word by word (lane <-> word, 4 levels x 4 word segments = 16
-// independent loads in flight), popcounts, and writes one exact integer; levels whose K1 count is zero
-// are skipped without touching their mask words. No atomics, no dependent load chain.
+// KJI mask: one block per column. The mask layout is opaque but identical for every level, so a slab's
+// projected count is popcount(OR over its levels), word by word. Slabs without a cloudy level (most of them:
+// the K1 counts say which levels have cloud) get their zero from one thread each; the others are queued and
+// taken one per WARP, which ORs the slab's cloudy levels with 128-bit loads (lane <-> word group, up to eight
+// independent loads in flight), popcounts and writes one exact integer. No atomics on data, no dependent loads.
 template <typename T>
 __global__ void __launch_bounds__(256) cloud_project_kji_kernel(const uint32_t* mask, const int32_t* slab_idx,
                                                                 const int32_t* cnt, int mw, int nk, int nlev, double npts,
                                                                 int32_t* cntslab, T* A) {
-  constexpr int KB = 4, SEG = 4;
   extern __shared__ __align__(16) double sm[];
-  int* sidx = reinterpret_cast<int*>(sm);  // [nlev] slab_idx of this column
-  int* kend = sidx + nlev;                 // [nlev] exclusive end level of every slab
+  int* kend = reinterpret_cast<int*>(sm);  // [nlev] exclusive end level of every slab = min(running max of slab_idx, nk)
+  int* live_k = kend + nlev;               // [nk] 1 where the level has any cloudy cell (K1 count != 0)
+  int* queue = live_k + nk;                // [nlev] slabs that need the mask
+  __shared__ int wmax[32];
+  __shared__ int nqueue;
   const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int r = threadIdx.x; r < nlev; r += blockDim.x) sidx[r] = __ldg(slab_idx + (size_t)c * nlev + r);
-  __syncthreads();
+  const int32_t* cn = cnt ? cnt + (size_t)c * nk : nullptr;
+  if (threadIdx.x == 0) nqueue = 0;
+  for (int k = threadIdx.x; k < nk; k += blockDim.x) live_k[k] = cn ? (__ldg(cn + k) != 0) : 1;
+  // running maximum of slab_idx: warp-shuffle scan per 32 slabs, warp maxima through shared memory, carry per pass
+  int carry = 0;
+  for (int r0 = 0; r0 < nlev; r0 += blockDim.x) {      // block-uniform trip count
+    const int r = r0 + threadIdx.x;
+    int v = r < nlev ? __ldg(slab_idx + (size_t)c * nlev + r) : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v = max(v, up);
+    }
+    if (lane == 31) wmax[warp] = v;
+    __syncthreads();
+    int before = carry;
+    for (int w = 0; w < warp; ++w) before = max(before, wmax[w]);
+    if (r < nlev) kend[r] = min(max(v, before), nk);
+    for (int w = 0; w < nwarps; ++w) carry = max(carry, wmax[w]);
+    __syncthreads();
+  }
+  // one thread per slab: empty or cloud-free slabs are answered here, the rest are queued for the warps
   for (int r = threadIdx.x; r < nlev; r += blockDim.x) {
-    int m = 0;
-    for (int i = 0; i <= r; ++i) m = max(m, sidx[i]);
-    kend[r] = min(m, nk);
+    const int k0 = r ? kend[r - 1] : 0, k1 = kend[r];
+    bool any = false;
+    for (int k = k0; k < k1; ++k) any = any || live_k[k];
+    if (any) {
+      queue[atomicAdd(&nqueue, 1)] = r;     // order is irrelevant: slabs are independent
+    } else {
+      if (cntslab) cntslab[(size_t)c * nlev + r] = 0;
+      if (A) A[(size_t)c * nlev + r] = (T)0;
+    }
   }
   __syncthreads();
+  const int nq = nqueue;
   const uint32_t* m = mask + (size_t)c * nk * mw;
-  const int32_t* cn = cnt ? cnt + (size_t)c * nk : nullptr;
-  for (int r = warp; r < nlev; r += nwarps) {
+  const bool vec = (mw & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;   // block-uniform
+  for (int qi = warp; qi < nq; qi += nwarps) {
+    const int r = queue[qi];
     const int k0 = r ? kend[r - 1] : 0, k1 = kend[r];
     int n = 0;
-    if (k1 > k0) {
-      for (int w0 = 0; w0 < mw; w0 += 32 * SEG) {
-        uint32_t acc[SEG];
+    if (vec) {
+      constexpr int KB = 4, SEG = 2;
+      const int nvr = mw >> 2;                                        // 16-byte vectors per level
+      const bool packed = nvr < 32 && (32 % nvr) == 0;                // several levels per warp pass
+      const int rpp = packed ? 32 / nvr : 1;
+      const int roff = packed ? lane / nvr : 0, vpos = packed ? lane % nvr : lane;
+      const uint4* mv = reinterpret_cast<const uint4*>(m);
+      for (int v0 = 0; v0 < nvr; v0 += 32 * SEG) {
+        uint4 acc[SEG];
 #pragma unroll
-        for (int sg = 0; sg < SEG; ++sg) acc[sg] = 0u;
-        for (int kb = k0; kb < k1; kb += KB) {
-          uint32_t v[KB][SEG];
+        for (int sg = 0; sg < SEG; ++sg) acc[sg] = make_uint4(0u, 0u, 0u, 0u);
+        for (int kb = k0; kb < k1; kb += KB * rpp) {
+          uint4 v[KB][SEG];
 #pragma unroll
           for (int j = 0; j < KB; ++j) {
-            const int k = kb + j;
-            const bool live = k < k1 && (cn == nullptr || __ldg(cn + k) != 0);
+            const int k = kb + j * rpp + roff;
+            const bool live = k < k1 && live_k[k];
 #pragma unroll
             for (int sg = 0; sg < SEG; ++sg) {
-              const int w = w0 + sg * 32 + lane;
-              v[j][sg] = (live && w < mw) ? __ldg(m + (size_t)k * mw + w) : 0u;
+              const int p = v0 + sg * 32 + vpos;
+              v[j][sg] = (live && p < nvr) ? __ldg(mv + (size_t)k * nvr + p) : make_uint4(0u, 0u, 0u, 0u);
             }
           }
 #pragma unroll
           for (int j = 0; j < KB; ++j)
 #pragma unroll
-            for (int sg = 0; sg < SEG; ++sg) acc[sg] |= v[j][sg];
+            for (int sg = 0; sg < SEG; ++sg) {
+              acc[sg].x |= v[j][sg].x;
+              acc[sg].y |= v[j][sg].y;
+              acc[sg].z |= v[j][sg].z;
+              acc[sg].w |= v[j][sg].w;
+            }
+        }
+        if (packed) {                                                 // OR the level rows that shared this pass
+          for (int o = nvr; o < 32; o <<= 1) {
+            acc[0].x |= __shfl_xor_sync(0xffffffffu, acc[0].x, o);
+            acc[0].y |= __shfl_xor_sync(0xffffffffu, acc[0].y, o);
+            acc[0].z |= __shfl_xor_sync(0xffffffffu, acc[0].z, o);
+            acc[0].w |= __shfl_xor_sync(0xffffffffu, acc[0].w, o);
+          }
+          if (roff != 0) acc[0] = make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
-        for (int sg = 0; sg < SEG; ++sg) n += __popc(acc[sg]);
+        for (int sg = 0; sg < SEG; ++sg) n += __popc(acc[sg].x) + __popc(acc[sg].y) + __popc(acc[sg].z) + __popc(acc[sg].w);
       }
-      n = __reduce_add_sync(0xffffffffu, n);
+    } else {
+      for (int w = lane; w < mw; w += 32) {
+        uint32_t acc = 0u;
+        for (int k = k0; k < k1; ++k)
+          if (live_k[k]) acc |= __ldg(m + (size_t)k * mw + w);
+        n += __popc(acc);
+      }
     }
+    n = __reduce_add_sync(0xffffffffu, n);
     if (lane == 0) {
       if (cntslab) cntslab[(size_t)c * nlev + r] = n;
       if (A) A[(size_t)c * nlev + r] = (T)((double)n / npts);
@@ -286,9 +358,9 @@ int launch_cloud_projection(spc_handle h, const uint32_t* mask, const int32_t* s
   SPC_REQUIRE(per_col > 0, SPC_ERR_UNSUPPORTED, "no cloud mask format for this layout/shape");
   const double npts = (double)nx * (double)ny;
   if (layout == SPC_LAYOUT_KJI) {
-    const size_t smem = (size_t)2 * nlev * sizeof(int);
-    SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "nlev=%d too large", nlev);
-    cloud_project_kji_kernel<T><<<ncol, 256, smem, st>>>(mask, slab_idx, cnt, (int)(per_col / nk), nk, nlev, npts, cntslab, A);
+    const size_t smem = ((size_t)2 * nlev + nk) * sizeof(int);
+    SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "nlev=%d, nk=%d too large", nlev, nk);
+    cloud_project_kji_kernel<T><<<ncol, g_proj_threads ? g_proj_threads : (per_col / nk <= 128 ? 64 : 256), smem, st>>>(mask, slab_idx, cnt, (int)(per_col / nk), nk, nlev, npts, cntslab, A);
   } else {
     const size_t smem = (size_t)nlev * sizeof(int);
     SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "nlev=%d too large", nlev);
@@ -483,9 +555,10 @@ int check_gcm(const spc_gcm_cols* g, int couple_surface, const char* who) {
 extern "C" {
 
 // Tuning hook, not part of the public ABI (tools/step_probe.py only): threads per column CTA of K2 / K3.
-int spc_tune_profiles(int k2_threads, int k3_threads) {
-  if (k2_threads >= 32 && k2_threads <= kThreads) g_k2_threads = k2_threads & ~31;
-  if (k3_threads >= 32 && k3_threads <= kThreads) g_k3_threads = k3_threads & ~31;
+int spc_tune_profiles(int k2_threads, int k3_threads, int proj_threads) {
+  g_proj_threads = (proj_threads >= 32 && proj_threads <= 256) ? (proj_threads & ~31) : 0;
+  g_k2_threads = (k2_threads >= 32 && k2_threads <= kThreads) ? (k2_threads & ~31) : 0;
+  g_k3_threads = (k3_threads >= 32 && k3_threads <= kThreads) ? (k3_threads & ~31) : 0;
   return SPC_OK;
 }
 
@@ -503,8 +576,8 @@ int spc_gcm_to_les(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   SPC_REQUIRE(!((out->f_u || out->f_v || out->f_thl || out->f_qt || out->f_ql) && !les_prof), SPC_ERR_ARG,
               "spc_gcm_to_les: forcings requested but les_prof is NULL");
   if (gcm->ncol == 0) return SPC_OK;
-  const size_t smem = (size_t)6 * gcm->nlev * sizeof(double);
-  SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_gcm_to_les: nlev=%d too large", gcm->nlev);
+  const size_t smem = ((size_t)6 * gcm->nlev + nk) * sizeof(double);
+  SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_gcm_to_les: nlev=%d, nk=%d too large", gcm->nlev, nk);
   spc::DeviceGuard guard(h->device);
   K2Args a;
   a.g = to_ptrs(gcm);
@@ -512,8 +585,9 @@ int spc_gcm_to_les(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   a.o = *out;
   a.dt = dt; a.factor = factor; a.nk = nk; a.couple_surface = couple_surface;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (gcm->dtype == SPC_F32) gcm_to_les_kernel<float><<<gcm->ncol, g_k2_threads, smem, st>>>(a);
-  else gcm_to_les_kernel<double><<<gcm->ncol, g_k2_threads, smem, st>>>(a);
+  const int threads = column_threads(g_k2_threads, std::max(gcm->nlev + 1, nk));
+  if (gcm->dtype == SPC_F32) gcm_to_les_kernel<float><<<gcm->ncol, threads, smem, st>>>(a);
+  else gcm_to_les_kernel<double><<<gcm->ncol, threads, smem, st>>>(a);
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
 }
@@ -559,8 +633,9 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   a.n_peers = out->tend_peers ? out->n_peers : 0;
   for (int p = 0; p < a.n_peers; ++p) a.peers[p] = out->tend_peers[p];
   a.peer_off = (size_t)out->peer_col0 * SPC_NTEND * gcm->nlev;
-  if (gcm->dtype == SPC_F32) les_to_gcm_kernel<float><<<gcm->ncol, g_k3_threads, smem, st>>>(a);
-  else les_to_gcm_kernel<double><<<gcm->ncol, g_k3_threads, smem, st>>>(a);
+  const int threads = column_threads(g_k3_threads, std::max(gcm->nlev + 1, nk));
+  if (gcm->dtype == SPC_F32) les_to_gcm_kernel<float><<<gcm->ncol, threads, smem, st>>>(a);
+  else les_to_gcm_kernel<double><<<gcm->ncol, threads, smem, st>>>(a);
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
 }

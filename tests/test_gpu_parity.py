@@ -61,6 +61,8 @@ def check_step(case, ref, slab, frc, tnd, rtol, mask_expected=True):
     (2, 10, 10, 20, 19, np.float32),      # slab bytes not a multiple of 16: generic path
     (2, 40, 40, 24, 91, np.float32),      # ragged: slab = 1 full + 1 partial TMA chunk
     (2, 24, 20, 16, 19, np.float64),      # ragged float64 chunks
+    (2, 48, 48, 40, 91, np.float32),      # three 4 KB sub-blocks per slab: 24 mask vectors per level (not a divisor of 32)
+    (2, 32, 16, 160, 137, np.float32),    # 2 KB slabs: one partial sub-block, 8 mask vectors per level, four levels per warp pass
 ])
 def test_coupling_step_matches_oracle(cpl, cuda_device, ncol, nx, ny, nk, nlev, dtype):
     case = cases.host_case(ncol, nx, ny, nk, nlev, dtype)
