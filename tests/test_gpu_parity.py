@@ -264,6 +264,16 @@ def test_set_les_state_bit_identical_to_host_generator(cpl, cuda_device):
             v = n(cpl.set_les_state(t(prof), 0.1, 1, nx, ny, seed=7, col0=0, sub=t(sub), clamp0=True, dtype=td))
             h = synth.les_state_volume(prof, 0.1, 1, nx, ny, seed=7, col0=0, sub=sub, clamp0=True, dtype=dtype)
             assert np.array_equal(v, h) and (v == 0).any() and (v > 0).any()
+            # every SUB / CLAMP instantiation, the reference amplitudes (spcpl.py:285-291), no noise, and an
+            # amplitude too close to the subnormals for the slab kernel's exact-scaling form (generic kernel)
+            for amp in (0.5, 2.5e-5, 0.0, 3e-305):
+                for use_sub, clamp in ((False, False), (True, False), (False, True), (True, True)):
+                    kw = dict(seed=11, col0=2, clamp0=clamp)
+                    v = n(cpl.set_les_state(t(prof - 300.0), amp, 2, nx, ny, sub=t(sub - 300.0) if use_sub else None,
+                                            dtype=td, **kw))
+                    h = synth.les_state_volume(prof - 300.0, amp, 2, nx, ny, sub=(sub - 300.0) if use_sub else None,
+                                               dtype=dtype, **kw)
+                    assert np.array_equal(v, h), (amp, use_sub, clamp)
 
 
 def test_errors_are_loud(cpl, cuda_device):
