@@ -317,6 +317,14 @@ def run_b200(args):
                     "note": "NOT the design point: LES volumes copied from pinned host memory every step (PCIe-bound)"}
         del hvols_host, hvols_dev, hpipe
 
+    # ---- optional: the same device step replayed from a CUDA graph (one launch per step) ----
+    graph_leg = None
+    if args.graph and (world == 1 or gather == "nccl"):
+        pipe.capture(DT, F_LES, F_GCM)
+        ms_g = timed(pipe.step_graph, args.steps, args.warmup)
+        graph_leg = {"value": ncol_total / (ms_g * 1e-3), "unit": "columns/s", "ms_per_step": ms_g,
+                     "note": "device-resident step replayed from one CUDA graph (K2, K1, projection, K3 captured once)"}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -358,6 +366,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
                 "note": "GCM profiles H2D (pinned) + tendencies D2H every step; LES volumes are device-resident LES state"},
         "e2e_host_volumes": host_vol,
+        "cuda_graph": graph_leg,
         "gpu_launches": launches,
         "clocks": clocks,
     }
@@ -385,6 +394,8 @@ def main():
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-cols", type=int, default=4, help="distinct columns per reference worker")
     ap.add_argument("--ref-reps", type=int, default=8, help="passes over them per step")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="skip the extra leg that times the device step replayed from a CUDA graph")
     ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p", "p2p-owner"],
                     help="multi-GPU tendency gather: NCCL all_gather, or fused into K3 (NVLink peer stores)")
     args = ap.parse_args()

@@ -161,6 +161,9 @@ class CouplingPipeline(object):
             self.tend_all = torch.zeros((ncol * self.world, 7, nlev), dtype=dtype, device=dev) if self.gather else self.tend
         self.tend_host = torch.empty(self.tend_all.shape, dtype=dtype, pin_memory=True)
         self.k1_events = None       # optional [(start, end)] CUDA events around K1 (bench roofline)
+        self._graph = None          # CUDA graph of step_device (capture())
+        self._graph_frc = self._graph_args = None
+        self._graph_launches = 0
 
     # LES side --------------------------------------------------------------------------------
     def attach_les(self, vols, aux):
@@ -209,11 +212,46 @@ class CouplingPipeline(object):
         self.tendencies(frc, dt, f_gcm)
         return frc
 
+    # CUDA graph of the device step ---------------------------------------------------------------
+    def capture(self, dt=900.0, f_les=1.0, f_gcm=1.0, warmup=2):
+        """Records K2 -> K1 -> cloud projection -> K3 (-> NCCL all_gather) once into a CUDA graph, so that a step is
+        one graph launch instead of four calls through the C ABI. Worth it for small column batches, where the
+        step is launch-bound; at thousands of columns the host is far ahead of K1 anyway. All buffers of the
+        step (forcings, slab means, mask, tendencies) become static: `step_graph()` returns the same tensors
+        every time. The fused NVLink gather keeps its eager path (its device barrier is not captured)."""
+        if self.gather and self.gather_mode != "nccl":
+            raise RuntimeError("capture() supports the single-GPU step and the NCCL gather, not gather=%r" % self.gather_mode)
+        if self.k1_events is not None:
+            raise RuntimeError("K1 event timing must be off during capture")
+        cur = torch.cuda.current_stream(self.cpl.device)
+        side = torch.cuda.Stream(self.cpl.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):          # warm-up off the capture: lazy kernel attributes, allocator pools
+            for _ in range(warmup):
+                self.step_device(dt, f_les, f_gcm)
+        cur.wait_stream(side)
+        l0 = self.cpl.launches
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            frc = self.step_device(dt, f_les, f_gcm)
+        self._graph, self._graph_frc, self._graph_launches = graph, frc, self.cpl.launches - l0
+        self._graph_args = (dt, f_les, f_gcm)
+        return graph
+
+    def step_graph(self):
+        """Replays the captured step on the current stream; returns the (static) forcing tensors."""
+        self._graph.replay()
+        self.cpl.launches += self._graph_launches
+        return self._graph_frc
+
     def step_host(self, dt=900.0, f_les=1.0, f_gcm=1.0, owner=0):
         """The step as the host GCM sees it: GCM profiles in pinned host memory in, tendencies in
         pinned host memory out on the rank that owns the GCM. Synchronises before returning."""
         self.staging.upload()
-        frc = self.step_device(dt, f_les, f_gcm)
+        if self._graph is not None and self._graph_args == (dt, f_les, f_gcm):
+            frc = self.step_graph()
+        else:
+            frc = self.step_device(dt, f_les, f_gcm)
         if self.rank == owner:
             self.tend_host.copy_(self.tend_all, non_blocking=True)
         torch.cuda.current_stream(self.cpl.device).synchronize()

@@ -367,3 +367,41 @@ def _abi_code(name):
     import conftest
     src = open(os.path.join(conftest.ROOT, "include", "spcpl_b200.h")).read()
     return int(re.search(name + r"\s*=\s*(-?\d+)", src).group(1))
+
+
+@pytest.mark.parametrize("ncol", [2, 48])
+def test_cuda_graph_step_is_bit_identical(cpl, cuda_device, ncol):
+    """CouplingPipeline.capture(): the replayed graph (K2 -> K1 -> projection -> K3) gives the bits of the eager step,
+    also after the inputs changed in place (new GCM profiles uploaded, LES volumes rewritten)."""
+    import torch
+    from sp_coupler_b200 import synth
+    from sp_coupler_b200.pipeline import CouplingPipeline
+    nx, nk, nlev = 16, 160, 91
+    zf, zh = synth.les_grid(nk)
+    gcm = synth.make_gcm_columns(ncol, nlev, seed=3, dtype=np.float32)
+    aux = {k: torch.from_numpy(v).to(cuda_device) for k, v in synth.make_les_aux(ncol, nk, seed=3, dtype=np.float32).items()}
+    pipes = []
+    for _ in range(2):
+        p = CouplingPipeline(cpl, zf, zh, ncol, nlev, torch.float32)
+        p.staging.fill_host(gcm)
+        p.staging.upload()
+        p.attach_les(synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=3), aux)
+        p.les_profiles()
+        pipes.append(p)
+    eager, graphed = pipes
+    graphed.capture(900.0, 1.0, 0.5)
+    l0 = cpl.launches
+    for it in range(3):
+        if it == 1:       # change the inputs in place: both pipelines must follow
+            gcm2 = synth.make_gcm_columns(ncol, nlev, seed=9, dtype=np.float32)
+            for p in pipes:
+                p.staging.fill_host(gcm2)
+                p.vols[1].mul_(1.001)
+        f1, t1 = eager.step_host(900.0, 1.0, 0.5)
+        f2, t2 = graphed.step_host(900.0, 1.0, 0.5)
+        assert torch.equal(t1, t2)
+        for k in ("f_u", "f_v", "f_thl", "f_qt", "f_ql", "f_ps", "slab_idx"):
+            assert torch.equal(f1[k], f2[k]), k
+        for k in ("prof", "cnt", "mask"):
+            assert torch.equal(eager.slab[k], graphed.slab[k]), k
+    assert cpl.launches - l0 == 2 * 3 * 4      # both paths count K2, K1, projection, K3 per step
