@@ -108,12 +108,12 @@ def _cpu_sample_inputs(ncols, nx, ny, nk, nlev, np_dtype, seed, col0=0):
     return zf, zh, gcm, aux, vols
 
 
-def _cpu_pass(inp):
+def _cpu_pass(inp, layout=0):
     """The reference's per-step work for a block of columns, as the numpy port does it: slab means
     + cloud count (DALES side) and set_les_forcings / set_gcm_tendencies (spcpl.py)."""
     from oracle import numpy_batched as nb
     zf, zh, gcm, aux, vols = inp
-    return nb.coupling_step(gcm, zf, zh, vols, aux, aux["PS"], DT, F_LES, F_GCM, True, 0.0, 0, accumulate="native")
+    return nb.coupling_step(gcm, zf, zh, vols, aux, aux["PS"], DT, F_LES, F_GCM, True, 0.0, layout, accumulate="native")
 
 
 def _worker_init(cfg, ncols, seed):
@@ -177,11 +177,12 @@ def cpu_baseline(args, vols_dev, gcm_host, aux_host, zf, zh, budget_s=12.0, ncol
     from sp_coupler_b200.constants import LES_FIELDS
     vols = {f: v[:ncols].cpu().numpy() for f, v in zip(LES_FIELDS, vols_dev)}
     inp = (zf, zh, {k: v[:ncols] for k, v in gcm_host.items()}, {k: v[:ncols] for k, v in aux_host.items()}, vols)
-    _cpu_pass(inp)
+    lay = 1 if args.layout == "ijk" else 0
+    _cpu_pass(inp, lay)
     t0 = time.perf_counter()
     passes = 0
     while True:
-        _cpu_pass(inp)
+        _cpu_pass(inp, lay)
         passes += 1
         el = time.perf_counter() - t0
         if el >= budget_s or passes >= 200:
@@ -243,6 +244,10 @@ def run_b200(args):
     pipe.staging.fill_host(gcm_host)
     pipe.staging.upload()
     vols = synth.device_les_volumes(cpl, gcm_host, zf, nx, ny, seed=42 + 2, dtype=tdt, col0=col0)
+    if args.layout == "ijk":     # the (itot, jtot, ktot) C-order view OMUSE hands to Python: k fastest
+        for i in range(len(vols)):
+            vols[i] = vols[i].permute(0, 3, 2, 1).contiguous()
+        pipe.layout = "ijk"
     aux = {k: torch.from_numpy(v).to(dev) for k, v in aux_host.items()}
     pipe.attach_les(vols, aux)
     pipe.les_profiles()                      # first-step slab means (spcpl.py:302-308)
@@ -297,7 +302,7 @@ def run_b200(args):
     host_vol = None
     if world == 1 and args.host_volume_cols > 0:
         hc = min(args.host_volume_cols, ncol)
-        hpipe = CouplingPipeline(cpl, zf, zh, hc, nlev, tdt, couple_surface=True)
+        hpipe = CouplingPipeline(cpl, zf, zh, hc, nlev, tdt, couple_surface=True, layout=args.layout)
         hpipe.staging.fill_host({k: v[:hc] for k, v in gcm_host.items()})
         hvols_host = [torch.empty((hc,) + tuple(v.shape[1:]), dtype=tdt, pin_memory=True) for v in vols]
         for hv, v in zip(hvols_host, vols):
@@ -343,7 +348,7 @@ def run_b200(args):
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            if tj.get("config") == args.config and tj.get("ncol") == ncol:
+            if tj.get("config") == args.config and tj.get("ncol") == ncol and args.layout == "kji":
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -354,11 +359,11 @@ def run_b200(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config, ncol), "ncol_total": ncol_total,
-                   "storage_dtype": dts, "arithmetic": "f64", "l2": "inputs larger than L2 (%.1f GB of LES volumes per GPU "
+                   "storage_dtype": dts, "arithmetic": "f64", "layout": args.layout, "l2": "inputs larger than L2 (%.1f GB of LES volumes per GPU "
                    "streamed once per step; no reuse between steps)" % (bpc * ncol / 1e9),
                    "parallelism": ("columns sharded x%d, tendencies %s" % (world, "all_gather (NCCL)" if gather == "nccl" else "gathered by K3 itself (%s): NVLink peer stores into symmetric memory + device barrier" % gather)) if world > 1 else "1 GPU",
                    "step": "K2 gcm_to_les -> K1 slab_reduce -> K3 les_to_gcm"},
-        "roofline": {"kernel": "slab_reduce_tma_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline": {"kernel": "slab_reduce_tma_kernel" if args.layout == "kji" else "slab_reduce_ijk_tma_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0, "k1_ms": k1_ms, "k1_share_of_step": k1_ms / ms_step,
                      "alg_bytes_per_launch": bpc * ncol},
@@ -394,6 +399,8 @@ def main():
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-cols", type=int, default=4, help="distinct columns per reference worker")
     ap.add_argument("--ref-reps", type=int, default=8, help="passes over them per step")
+    ap.add_argument("--layout", default="kji", choices=["kji", "ijk"],
+                    help="memory order of the LES volumes: kji = [ncol][nk][ny][nx] (DALES), ijk = [ncol][nx][ny][nk] (OMUSE view)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="skip the extra leg that times the device step replayed from a CUDA graph")
     ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p", "p2p-owner"],

@@ -192,17 +192,15 @@ __device__ double integral_w(double a, double b, const double* z, int n, const d
 // the K1 counts say which levels have cloud) get their zero from one thread each; the others are queued and
 // taken one per WARP, which ORs the slab's cloudy levels with 128-bit loads (lane <-> word group, up to eight
 // independent loads in flight), popcounts and writes one exact integer. No atomics on data, no dependent loads.
+// Prologue shared by both mask layouts: kend[r] = min(running max of slab_idx, nk), live_k[k] = level k has a cloudy
+// cell (K1 count != 0; all levels when no counts are given); slabs that are empty or cloud-free get their zero here,
+// the others are queued. Returns the queue length (after a block barrier).
 template <typename T>
-__global__ void __launch_bounds__(256) cloud_project_kji_kernel(const uint32_t* mask, const int32_t* slab_idx,
-                                                                const int32_t* cnt, int mw, int nk, int nlev, double npts,
-                                                                int32_t* cntslab, T* A) {
-  extern __shared__ __align__(16) double sm[];
-  int* kend = reinterpret_cast<int*>(sm);  // [nlev] exclusive end level of every slab = min(running max of slab_idx, nk)
-  int* live_k = kend + nlev;               // [nk] 1 where the level has any cloudy cell (K1 count != 0)
-  int* queue = live_k + nk;                // [nlev] slabs that need the mask
+__device__ __forceinline__ int cloud_slab_queue(const int32_t* slab_idx, const int32_t* cnt, int nk, int nlev, int c,
+                                                int* kend, int* live_k, int* queue, int32_t* cntslab, T* A) {
   __shared__ int wmax[32];
   __shared__ int nqueue;
-  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int32_t* cn = cnt ? cnt + (size_t)c * nk : nullptr;
   if (threadIdx.x == 0) nqueue = 0;
   for (int k = threadIdx.x; k < nk; k += blockDim.x) live_k[k] = cn ? (__ldg(cn + k) != 0) : 1;
@@ -224,7 +222,7 @@ __global__ void __launch_bounds__(256) cloud_project_kji_kernel(const uint32_t* 
     for (int w = 0; w < nwarps; ++w) carry = max(carry, wmax[w]);
     __syncthreads();
   }
-  // one thread per slab: empty or cloud-free slabs are answered here, the rest are queued for the warps
+  // one thread per slab: empty or cloud-free slabs are answered here, the rest are queued
   for (int r = threadIdx.x; r < nlev; r += blockDim.x) {
     const int k0 = r ? kend[r - 1] : 0, k1 = kend[r];
     bool any = false;
@@ -237,7 +235,19 @@ __global__ void __launch_bounds__(256) cloud_project_kji_kernel(const uint32_t* 
     }
   }
   __syncthreads();
-  const int nq = nqueue;
+  return nqueue;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cloud_project_kji_kernel(const uint32_t* mask, const int32_t* slab_idx,
+                                                                const int32_t* cnt, int mw, int nk, int nlev, double npts,
+                                                                int32_t* cntslab, T* A) {
+  extern __shared__ __align__(16) double sm[];
+  int* kend = reinterpret_cast<int*>(sm);  // [nlev] exclusive end level of every slab
+  int* live_k = kend + nlev;               // [nk] 1 where the level has any cloudy cell
+  int* queue = live_k + nk;                // [nlev] slabs that need the mask
+  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int nq = cloud_slab_queue<T>(slab_idx, cnt, nk, nlev, c, kend, live_k, queue, cntslab, A);
   const uint32_t* m = mask + (size_t)c * nk * mw;
   const bool vec = (mw & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;   // block-uniform
   for (int qi = warp; qi < nq; qi += nwarps) {
@@ -332,7 +342,64 @@ __device__ __forceinline__ void project_cloud_rows(const uint32_t* m, const int3
   }
 }
 
-// IJK mask: one block per column (project_cloud_rows above).
+// IJK mask, nk <= 256: one block per column. A thread keeps the mask words of ROWS horizontal points in registers
+// (one coalesced read of the column's mask), then the block walks the queued (cloudy) slabs: the slab's bit range is
+// tested against the 1-2 words it touches (the word loop is unrolled and skipped by a block-uniform test), the points
+// with any cloud are counted with a warp reduction and one shared-memory add per warp and slab. Exact integers.
+template <typename T, int KW, int ROWS>
+__global__ void __launch_bounds__(256) cloud_project_ijk_reg_kernel(const uint32_t* mask, const int32_t* slab_idx,
+                                                                    const int32_t* cnt, int kw, int S, size_t per_col, int nk,
+                                                                    int nlev, double npts, int32_t* cntslab, T* A) {
+  extern __shared__ __align__(16) double sm[];
+  int* kend = reinterpret_cast<int*>(sm);
+  int* live_k = kend + nlev;
+  int* queue = live_k + nk;
+  int* cq = queue + nlev;                  // [nlev] projected count of every queued slab
+  const int c = blockIdx.x, lane = threadIdx.x & 31;
+  const int nq = cloud_slab_queue<T>(slab_idx, cnt, nk, nlev, c, kend, live_k, queue, cntslab, A);
+  for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) cq[qi] = 0;
+  __syncthreads();
+  const uint32_t* m = mask + (size_t)c * per_col;
+  for (int row0 = 0; row0 < S && nq > 0; row0 += blockDim.x * ROWS) {      // block-uniform
+    uint32_t w[ROWS][KW];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+      const int row = row0 + i * blockDim.x + threadIdx.x;
+#pragma unroll
+      for (int q = 0; q < KW; ++q) w[i][q] = (row < S && q < kw) ? __ldg(m + (size_t)row * kw + q) : 0u;
+    }
+    for (int qi = 0; qi < nq; ++qi) {
+      const int r = queue[qi];
+      const int k0 = r ? kend[r - 1] : 0, k1 = kend[r];
+      const int q_lo = k0 >> 5, q_hi = (k1 - 1) >> 5;
+      uint32_t any[ROWS];
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) any[i] = 0u;
+#pragma unroll
+      for (int q = 0; q < KW; ++q) {
+        if (q >= q_lo && q <= q_hi) {                                       // block-uniform
+          const int lo = max(k0 - (q << 5), 0), hi = min(k1 - (q << 5), 32);   // bit range [lo, hi) of word q
+          const uint32_t range = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+#pragma unroll
+          for (int i = 0; i < ROWS; ++i) any[i] |= w[i][q] & range;
+        }
+      }
+      int n = 0;
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) n += (any[i] != 0u);
+      n = __reduce_add_sync(0xffffffffu, n);
+      if (lane == 0 && n) atomicAdd(&cq[qi], n);
+    }
+  }
+  __syncthreads();
+  for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
+    const int r = queue[qi];
+    if (cntslab) cntslab[(size_t)c * nlev + r] = cq[qi];
+    if (A) A[(size_t)c * nlev + r] = (T)((double)cq[qi] / npts);
+  }
+}
+
+// IJK mask, any nk: one block per column (project_cloud_rows above).
 template <typename T>
 __global__ void __launch_bounds__(kThreads) cloud_project_ijk_kernel(const uint32_t* mask, const int32_t* slab_idx, int kw, int S,
                                                                      size_t per_col, int nk, int nlev, double npts,
@@ -362,10 +429,22 @@ int launch_cloud_projection(spc_handle h, const uint32_t* mask, const int32_t* s
     SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "nlev=%d, nk=%d too large", nlev, nk);
     cloud_project_kji_kernel<T><<<ncol, g_proj_threads ? g_proj_threads : (per_col / nk <= 128 ? 64 : 256), smem, st>>>(mask, slab_idx, cnt, (int)(per_col / nk), nk, nlev, npts, cntslab, A);
   } else {
-    const size_t smem = (size_t)nlev * sizeof(int);
-    SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "nlev=%d too large", nlev);
-    cloud_project_ijk_kernel<T><<<ncol, kThreads, smem, st>>>(mask, slab_idx, (nk + 31) / 32, nx * ny, per_col, nk, nlev, npts,
-                                                             cntslab, A);
+    const int kw = (nk + 31) / 32, S = nx * ny;
+    const size_t smem_reg = ((size_t)3 * nlev + nk) * sizeof(int);
+    if (kw <= 8 && smem_reg <= 48 * 1024) {
+#define SPC_IJK_PROJ(KW, ROWS)                                                                                          \
+  cloud_project_ijk_reg_kernel<T, KW, ROWS><<<ncol, 256, smem_reg, st>>>(mask, slab_idx, cnt, kw, S, per_col, nk, nlev, npts, \
+                                                                         cntslab, A)
+      if (kw <= 2) SPC_IJK_PROJ(2, 16);
+      else if (kw <= 4) SPC_IJK_PROJ(4, 16);
+      else if (kw == 5) SPC_IJK_PROJ(5, 16);
+      else SPC_IJK_PROJ(8, 8);
+#undef SPC_IJK_PROJ
+    } else {
+      const size_t smem = (size_t)nlev * sizeof(int);
+      SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "nlev=%d too large", nlev);
+      cloud_project_ijk_kernel<T><<<ncol, kThreads, smem, st>>>(mask, slab_idx, kw, S, per_col, nk, nlev, npts, cntslab, A);
+    }
   }
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;

@@ -80,7 +80,8 @@ def test_coupling_step_matches_oracle(cpl, cuda_device, ncol, nx, ny, nk, nlev, 
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("shape", [(2, 16, 12, 160, 19), (2, 6, 5, 21, 19), (3, 32, 32, 40, 91)])
+@pytest.mark.parametrize("shape", [(2, 16, 12, 160, 19), (2, 6, 5, 21, 19), (3, 32, 32, 40, 91),
+                                   (2, 4, 4, 288, 19)])     # nine mask words per point: generic projection kernel
 def test_ijk_layout_matches_oracle(cpl, cuda_device, dtype, shape):
     """[ncol][nx][ny][nk] (OMUSE view, k fastest): whole step incl. the projected cloud cover from
     the per-point bit mask; odd nk exercises the scalar (non-vectorised) variant."""
