@@ -348,8 +348,8 @@ def run_b200(args):
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            if tj.get("config") == args.config and tj.get("ncol") == ncol and args.layout == "kji":
-                traffic = tj.get("dram_bytes_per_launch")
+            if tj.get("config") == args.config and tj.get("ncol") == ncol:
+                traffic = (tj if args.layout == "kji" else tj.get("ijk", {})).get("dram_bytes_per_launch")
         except Exception:
             pass
     h2d = pipe.staging.nbytes
