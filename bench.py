@@ -324,7 +324,7 @@ def run_b200(args):
 
     # ---- optional: the same device step replayed from a CUDA graph (one launch per step) ----
     graph_leg = None
-    if args.graph and (world == 1 or gather == "nccl"):
+    if args.graph and world == 1:
         pipe.capture(DT, F_LES, F_GCM)
         ms_g = timed(pipe.step_graph, args.steps, args.warmup)
         graph_leg = {"value": ncol_total / (ms_g * 1e-3), "unit": "columns/s", "ms_per_step": ms_g,

@@ -214,13 +214,15 @@ class CouplingPipeline(object):
 
     # CUDA graph of the device step ---------------------------------------------------------------
     def capture(self, dt=900.0, f_les=1.0, f_gcm=1.0, warmup=2):
-        """Records K2 -> K1 -> cloud projection -> K3 (-> NCCL all_gather) once into a CUDA graph, so that a step is
+        """Records K2 -> K1 -> cloud projection -> K3 of a single-rank step once into a CUDA graph, so that a step is
         one graph launch instead of four calls through the C ABI. Worth it for small column batches, where the
         step is launch-bound; at thousands of columns the host is far ahead of K1 anyway. All buffers of the
         step (forcings, slab means, mask, tendencies) become static: `step_graph()` returns the same tensors
-        every time. The fused NVLink gather keeps its eager path (its device barrier is not captured)."""
-        if self.gather and self.gather_mode != "nccl":
-            raise RuntimeError("capture() supports the single-GPU step and the NCCL gather, not gather=%r" % self.gather_mode)
+        every time. Sharded runs (tendency gather on) keep the eager path."""
+        if self.gather:
+            raise RuntimeError("capture() records the single-rank step; with a tendency gather (gather=%r) run it eagerly "
+                               "(capturing the collective hung in testing and the fused gather's barrier is not capturable)"
+                               % self.gather_mode)
         if self.k1_events is not None:
             raise RuntimeError("K1 event timing must be off during capture")
         cur = torch.cuda.current_stream(self.cpl.device)
