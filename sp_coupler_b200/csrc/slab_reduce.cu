@@ -186,21 +186,26 @@ __global__ void __launch_bounds__(R::kWarps * 32, 1) slab_reduce_tma_kernel(cons
   const long long nq = nslab * a.nch;  // chunks this warp streams
   const uint64_t pol = l2_evict_first_policy();
 
+  // (field, slab-within-field) of a slab index advance incrementally with the stride: no 64-bit division per slab
+  const int f0 = (int)(g0 / a.per_field);
+  const long long rem0 = g0 - (long long)f0 * a.per_field;
   // producer state (lane 0): next chunk to issue
-  long long pi = 0;  // slab ordinal
-  int pj = 0;        // chunk within slab
+  int pf = f0;            // field of the slab being fetched
+  long long prem = rem0;  // its index within the field (= c*nk + k)
+  int pj = 0;             // chunk within slab
   auto issue = [&](int stage) {
-    const long long g = g0 + pi * gstride;
-    const int f = (int)(g / a.per_field);
-    const long long rem = g - (long long)f * a.per_field;
-    const uint8_t* src = static_cast<const uint8_t*>(field_ptr(a, f)) + (size_t)rem * a.slab_bytes + (size_t)pj * kChunk;
+    const uint8_t* src = static_cast<const uint8_t*>(field_ptr(a, pf)) + (size_t)prem * a.slab_bytes + (size_t)pj * kChunk;
     const int bytes = min(kChunk, a.slab_bytes - pj * kChunk);
     const uint32_t bar = wbar_s + 8 * stage;
     mbar_arrive_expect_tx(bar, (uint32_t)bytes);
     tma_bulk_g2s(wbuf_s + stage * kChunk, src, (uint32_t)bytes, bar, pol);
     if (++pj == a.nch) {
       pj = 0;
-      ++pi;
+      prem += gstride;
+      while (prem >= a.per_field) {
+        prem -= a.per_field;
+        ++pf;
+      }
     }
   };
   if (lane == 0) {
@@ -211,10 +216,10 @@ __global__ void __launch_bounds__(R::kWarps * 32, 1) slab_reduce_tma_kernel(cons
   int stage = 0;
   uint32_t parity = 0;
   long long q = 0;
+  int f = f0;
+  long long rem = rem0;  // = c*nk + k
   for (long long i = 0; i < nslab; ++i) {
     const long long g = g0 + i * gstride;
-    const int f = (int)(g / a.per_field);
-    const long long rem = g - (long long)f * a.per_field;  // = c*nk + k
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     int cnt = 0;
     const bool is_ql = (f == SPC_QL) && (a.cnt != nullptr || a.mask != nullptr);
@@ -249,6 +254,11 @@ __global__ void __launch_bounds__(R::kWarps * 32, 1) slab_reduce_tma_kernel(cons
       if (lane == 0) a.cnt[rem] = c;
     }
     if (lane == 0) a.prof[g] = s / (double)a.S;
+    rem += gstride;
+    while (rem >= a.per_field) {
+      rem -= a.per_field;
+      ++f;
+    }
   }
 }
 
