@@ -262,6 +262,90 @@ __global__ void __launch_bounds__(R::kWarps * 32, 1) slab_reduce_tma_kernel(cons
   }
 }
 
+// 4 KB slabs (32 x 32 float32): a TMA copy of one slab is only half the size the copy engine likes, and twice as
+// many warps are needed to keep the same bytes in flight. This variant streams PAIRS of consecutive slabs as one
+// 8 KB copy per warp (12 warps), reduces the two halves into separate accumulators, hands the stage back and only
+// then runs the two slab epilogues (shuffle butterflies, divide, stores), so they overlap with the next fetch.
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) slab_reduce_tma_pair_kernel(const K1Args a) {
+  constexpr int kChunk = 2 * kSubBytes;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * kChunk);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* wbuf = smem + (size_t)warp * kChunk;
+  const uint32_t wbuf_s = smem_u32(wbuf);
+  const uint32_t bar = smem_u32(bars + warp);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  // pair p = slabs 2p, 2p+1 (same field: per_field is even on this path); warp w of the grid takes pairs w, w+nwarps, ...
+  const long long nwarps = (long long)gridDim.x * WARPS, npairs = a.total >> 1, half_field = a.per_field >> 1;
+  const long long p0 = (long long)blockIdx.x * WARPS + warp;
+  if (p0 >= npairs) return;
+  const long long npair = (npairs - p0 + nwarps - 1) / nwarps;
+  const uint64_t pol = l2_evict_first_policy();
+  int f = (int)(p0 / half_field);               // consumer cursor (every lane carries it): field, pair within the field
+  long long rem = p0 - (long long)f * half_field;
+  int pf = f;                                   // producer cursor (lane 0 advances it when it issues a copy)
+  long long prem = rem;
+  auto issue = [&]() {
+    const uint8_t* src = static_cast<const uint8_t*>(field_ptr(a, pf)) + (size_t)prem * kChunk;
+    mbar_arrive_expect_tx(bar, (uint32_t)kChunk);
+    tma_bulk_g2s(wbuf_s, src, (uint32_t)kChunk, bar, pol);
+    prem += nwarps;
+    while (prem >= half_field) {
+      prem -= half_field;
+      ++pf;
+    }
+  };
+  if (lane == 0) issue();
+  uint32_t parity = 0;
+  for (long long i = 0; i < npair; ++i) {
+    const long long s0 = 2 * rem;               // first slab of the pair within the field (= c*nk + k)
+    const bool is_ql = (f == SPC_QL) && (a.cnt != nullptr || a.mask != nullptr);
+    double accA[4] = {0.0, 0.0, 0.0, 0.0}, accB[4] = {0.0, 0.0, 0.0, 0.0};
+    int cntA = 0, cntB = 0;
+    while (!mbar_try_wait(bar, parity)) {
+    }
+    parity ^= 1;
+    if (is_ql) {
+      const uint32_t bitsA = consume<T, true>(wbuf, kSubBytes >> 4, lane, accA, cntA, a.thr);
+      const uint32_t bitsB = consume<T, true>(wbuf + kSubBytes, kSubBytes >> 4, lane, accB, cntB, a.thr);
+      if (a.mask) {
+        a.mask[(size_t)s0 * 32 + lane] = bitsA;
+        a.mask[(size_t)(s0 + 1) * 32 + lane] = bitsB;
+      }
+    } else {
+      consume<T, false>(wbuf, kSubBytes >> 4, lane, accA, cntA, a.thr);
+      consume<T, false>(wbuf + kSubBytes, kSubBytes >> 4, lane, accB, cntB, a.thr);
+    }
+    __syncwarp();  // every lane is done reading the stage before it is refilled
+    if (lane == 0 && i + 1 < npair) issue();
+    const double sA = warp_sum((accA[0] + accA[1]) + (accA[2] + accA[3]));
+    const double sB = warp_sum((accB[0] + accB[1]) + (accB[2] + accB[3]));
+    if (is_ql && a.cnt) {
+      const int cA = warp_sum(cntA), cB = warp_sum(cntB);
+      if (lane == 0) {
+        a.cnt[s0] = cA;
+        a.cnt[s0 + 1] = cB;
+      }
+    }
+    if (lane == 0) {
+      const long long g = (long long)f * a.per_field + s0;
+      a.prof[g] = sA / (double)a.S;
+      a.prof[g + 1] = sB / (double)a.S;
+    }
+    rem += nwarps;
+    while (rem >= half_field) {
+      rem -= half_field;
+      ++f;
+    }
+  }
+}
+
 // Generic KJI path: any slab size / alignment. One warp per slab, scalar read-only loads.
 template <typename T>
 __global__ void __launch_bounds__(256) slab_reduce_generic_kernel(const K1Args a) {
@@ -716,6 +800,21 @@ int launch_tma(spc_handle h, const K1Args& a, cudaStream_t st) {
   X(1, 12, 8192, 1, false) X(2, 24, 4096, 1, false) X(3, 16, 4096, 3, false) X(4, 8, 8192, 2, false) \
   X(5, 8, 16384, 1, false) X(6, 16, 4096, 2, false) X(7, 12, 8192, 2, false) X(8, 12, 8192, 1, true)
 
+template <typename T>
+int launch_tma_pair(spc_handle h, const K1Args& a, cudaStream_t st) {
+  constexpr int W = 12;
+  const size_t smem = (size_t)W * 2 * kSubBytes + (size_t)W * 8;
+  static thread_local int configured_dev = -1;
+  if (configured_dev != h->device) {
+    SPC_CUDA(cudaFuncSetAttribute(slab_reduce_tma_pair_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_dev = h->device;
+  }
+  const long long want = ((a.total >> 1) + W - 1) / W;
+  const int grid = (int)std::min<long long>(h->num_sms, std::max<long long>(want, 1));
+  slab_reduce_tma_pair_kernel<T, W><<<grid, W * 32, smem, st>>>(a);
+  return SPC_OK;
+}
+
 int k1_variant_for(int slab_bytes) {
   if (g_k1_variant != 0) return g_k1_variant;
   return slab_bytes >= 8192 ? 1 : 2;
@@ -732,7 +831,10 @@ int k1_chunk_bytes(int slab_bytes) {
 
 template <typename T>
 int launch_kji(spc_handle h, const K1Args& a, bool fast, cudaStream_t st) {
-  if (fast) {
+  if (fast && a.slab_bytes == kSubBytes && a.per_field % 2 == 0 && (g_k1_variant == 0 || g_k1_variant == 9)) {
+    const int rc = launch_tma_pair<T>(h, a, st);   // 4 KB slabs in pairs (variant 9; 2 = one slab per copy)
+    if (rc) return rc;
+  } else if (fast) {
     int rc;
     switch (k1_variant_for(a.slab_bytes)) {
 #define X(id, w, c, s, b) case id: rc = launch_tma<T, Ring<w, c, s, b>>(h, a, st); break;
