@@ -296,7 +296,49 @@ def run_b200(args):
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in pipe.k1_events]))
     pipe.k1_events = None
     # ---- end-to-end leg: host GCM buffers in, host tendencies out, every step ----
-    ms_e2e = timed(lambda: pipe.step_host(DT, F_LES, F_GCM), args.steps, args.warmup)
+    e2e_note = "GCM profiles H2D (pinned) + tendencies D2H every step; LES volumes are device-resident LES state"
+    e2e_h2d = pipe.staging.nbytes
+    e2e_d2h = pipe.tend_host.numel() * pipe.tend_host.element_size()
+    exch = None
+    if world > 1 and args.host_exchange:
+        # the GCM lives in host memory of rank 0: every rank moves ITS columns' profiles / tendencies through one
+        # pinned host buffer shared by all ranks (all PCIe links at once), no device gather (pipeline.HostExchange)
+        from sp_coupler_b200.pipeline import HostExchange
+        try:
+            epipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, tdt, couple_surface=True, gather=False, layout=args.layout)
+            epipe.attach_les(vols, aux)
+            epipe.les_profiles()
+            ok = 1
+        except Exception as e:          # noqa: BLE001
+            sys.stderr.write("rank %d: e2e pipeline failed (%s)\n" % (rank, e))
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()):
+            try:
+                exch = HostExchange(epipe.staging, world, rank, owner=0, tag="bench")
+                ok = 1
+            except Exception as e:      # noqa: BLE001
+                sys.stderr.write("rank %d: shared pinned host buffer unavailable (%s)\n" % (rank, e))
+                ok = 0
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if not int(flag.item()):
+                exch = None
+    if exch is not None:
+        if rank == 0:      # the host GCM's profiles of ALL columns (identical to what each rank generated for itself)
+            exch.fill_inputs(synth.make_gcm_columns(ncol_total, nlev, seed=42 + 2, dtype=ndt, col0=0, ncol_total=ncol_total))
+        ms_e2e = timed(lambda: exch.step(epipe, DT, F_LES, F_GCM), args.steps, args.warmup)
+        e2e_h2d, e2e_d2h = world * epipe.staging.nbytes, world * epipe.tend.numel() * epipe.tend.element_size()
+        e2e_note = ("GCM profiles in / tendencies out of ONE pinned host buffer shared by all ranks (the host GCM's memory); "
+                    "every rank copies its own columns over its own PCIe link, no device gather; bytes are totals over ranks; "
+                    "LES volumes are device-resident LES state")
+        if rank == 0:      # same numbers as the device-gathered block of the `value` leg
+            torch.cuda.synchronize()
+            same = torch.equal(exch.out, pipe.tend_all.cpu())
+            e2e_note += "; tendencies identical to the device-gathered block: %s" % same
+    else:
+        ms_e2e = timed(lambda: pipe.step_host(DT, F_LES, F_GCM), args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
     # ---- for the record: the same step if the LES volumes lived in HOST memory (they do not) ----
     host_vol = None
@@ -352,8 +394,6 @@ def run_b200(args):
                 traffic = (tj if args.layout == "kji" else tj.get("ijk", {})).get("dram_bytes_per_launch")
         except Exception:
             pass
-    h2d = pipe.staging.nbytes
-    d2h = pipe.tend_host.numel() * pipe.tend_host.element_size()
     line = {
         "metric": METRIC, "value": ncol_total / (ms_step * 1e-3), "unit": "columns/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -367,9 +407,8 @@ def run_b200(args):
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0, "k1_ms": k1_ms, "k1_share_of_step": k1_ms / ms_step,
                      "alg_bytes_per_launch": bpc * ncol},
-        "e2e": {"value": ncol_total / (ms_e2e * 1e-3), "unit": "columns/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-                "note": "GCM profiles H2D (pinned) + tendencies D2H every step; LES volumes are device-resident LES state"},
+        "e2e": {"value": ncol_total / (ms_e2e * 1e-3), "unit": "columns/s", "h2d_bytes_per_step": e2e_h2d,
+                "d2h_bytes_per_step": e2e_d2h, "ms_per_step": ms_e2e, "note": e2e_note},
         "e2e_host_volumes": host_vol,
         "cuda_graph": graph_leg,
         "gpu_launches": launches,
@@ -401,6 +440,8 @@ def main():
     ap.add_argument("--ref-reps", type=int, default=8, help="passes over them per step")
     ap.add_argument("--layout", default="kji", choices=["kji", "ijk"],
                     help="memory order of the LES volumes: kji = [ncol][nk][ny][nx] (DALES), ijk = [ncol][nx][ny][nk] (OMUSE view)")
+    ap.add_argument("--no-host-exchange", dest="host_exchange", action="store_false",
+                    help="N>1: time e2e through the owner GPU (device gather + one D2H) instead of the shared pinned host buffer")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="skip the extra leg that times the device step replayed from a CUDA graph")
     ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p", "p2p-owner"],

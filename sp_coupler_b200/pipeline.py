@@ -109,6 +109,110 @@ class GcmScatter(object):
         return self.staging.dev
 
 
+class HostExchange(object):
+    """Host side of a sharded step when the GCM lives in HOST memory of one process (OpenIFS does): one pinned
+    host buffer shared by all ranks of the node (a /dev/shm mapping that every rank registers with CUDA).
+
+        GCM owner   writes every rank's packed input block into `inp[r]`, then publishes the step number
+        every rank  waits for it, copies ITS block host->device, runs the step on its columns, copies ITS
+                    tendency block device->host into `out[r*ncol:(r+1)*ncol]`, publishes "done"
+        GCM owner   waits for all ranks: `out` holds [world*ncol][7][nlev], no device gather, no collective
+
+    so the copies use every GPU's PCIe link at once instead of funnelling world*ncol columns through the
+    owner GPU's link (reference analogue: the master gathers every profile over its own channels,
+    spcpl.py:55-86, 535-542). Flags are int64 words in the same mapping (single writer each, monotonic).
+    Works on CPU tensors too (no registration) for the gloo tests."""
+
+    FLAG_WORDS = 64
+
+    def __init__(self, staging, world, rank, owner=0, group=None, register=True, tag="x", timeout_s=60.0):
+        import os
+        self.staging, self.world, self.rank, self.owner, self.group = staging, world, rank, owner, group
+        self.timeout_s = timeout_s
+        ncol, nlev, dtype = staging.ncol, staging.nlev, staging.dtype
+        esize = torch.empty((), dtype=dtype).element_size()
+        self.per_rank_in = staging.host_buf.numel()
+        self.per_rank_out = ncol * 7 * nlev
+        nin = world * self.per_rank_in * esize
+        nout = world * self.per_rank_out * esize
+        al = lambda n: (n + 4095) // 4096 * 4096
+        self._off_out = al(self.FLAG_WORDS * 8)
+        self._off_in = self._off_out + al(nout)
+        self.nbytes = self._off_in + al(nin)
+        path = "/dev/shm/spcpl_b200_%s_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "r"), tag)
+        if rank == owner:
+            with open(path, "wb") as f:
+                f.truncate(self.nbytes)
+        torch.distributed.barrier(group=group)
+        self.raw = torch.from_file(path, shared=True, size=self.nbytes, dtype=torch.uint8)
+        torch.distributed.barrier(group=group)
+        if rank == owner:
+            os.unlink(path)            # the mapping stays alive in every process; nothing is left behind
+        self.registered = False
+        if register and torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.raw.data_ptr(), self.nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError("cudaHostRegister of the shared host buffer failed (%s)" % (rc,))
+            self.registered = True
+        self.flags = self.raw[:self.FLAG_WORDS * 8].view(torch.int64)          # [0] inputs ready, [1+r] rank r done
+        self.out = self.raw[self._off_out:self._off_out + nout].view(dtype).view(world * ncol, 7, nlev)
+        self.inp = self.raw[self._off_in:self._off_in + nin].view(dtype).view(world, self.per_rank_in)
+        if rank == owner:
+            self.flags.zero_()
+        torch.distributed.barrier(group=group)
+        self.step_no = 0
+
+    def close(self):
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.raw.data_ptr())
+            self.registered = False
+
+    def fill_inputs(self, gcm_all):
+        """Owner only. gcm_all: dict of [world*ncol, ...] host arrays in global column order (what
+        gather_gcm_data fetched from the host GCM), packed per rank in GcmStaging order."""
+        st, ncol = self.staging, self.staging.ncol
+        for r in range(self.world):
+            off = 0
+            for n, h in st.host.items():
+                cnt = h.numel()
+                src = gcm_all[n][r * ncol:(r + 1) * ncol]
+                src = src if isinstance(src, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(src))
+                self.inp[r, off:off + cnt].view(h.shape).copy_(src)
+                off += cnt
+
+    def _wait(self, word, value):
+        import time
+        t0 = time.perf_counter()
+        while int(self.flags[word]) < value:
+            if time.perf_counter() - t0 > self.timeout_s:
+                raise RuntimeError("HostExchange: rank %d waited %.0f s for flag %d >= %d" % (self.rank, self.timeout_s, word, value))
+
+    def publish_inputs(self):
+        """Owner: the input blocks of the next step are in place."""
+        self.step_no += 1
+        self.flags[0] = self.step_no
+
+    def step(self, pipe, dt=900.0, f_les=1.0, f_gcm=1.0):
+        """One sharded host-to-host step (all ranks call it; the owner calls publish_inputs() first or passes
+        through here with inputs unchanged). Returns (forcings, out) - `out` is complete on the owner only."""
+        if self.rank == self.owner:
+            self.publish_inputs()
+        else:
+            self.step_no += 1
+        self._wait(0, self.step_no)
+        pipe.staging.dev_buf.copy_(self.inp[self.rank], non_blocking=True)
+        frc = pipe.step_device(dt, f_les, f_gcm)
+        lo = self.rank * pipe.ncol
+        self.out[lo:lo + pipe.ncol].copy_(pipe.tend, non_blocking=True)
+        if pipe.tend.is_cuda:
+            torch.cuda.current_stream(pipe.tend.device).synchronize()
+        self.flags[1 + self.rank] = self.step_no
+        if self.rank == self.owner:
+            for r in range(self.world):
+                self._wait(1 + r, self.step_no)
+        return frc, self.out
+
+
 class CouplingPipeline(object):
     """State + step of the GPU coupling path for this rank's columns."""
 

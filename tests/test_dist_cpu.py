@@ -92,3 +92,65 @@ def test_gcm_scatter_delivers_each_ranks_columns(tmp_path):
         lo, hi = shard_columns(NCOL, 2, rank)
         for k in full:
             assert np.array_equal(got[k], full[k][lo:hi]), (rank, k)
+
+
+class _OraclePipe(object):
+    """Stand-in for CouplingPipeline on CPU tensors: step_device() = the oracle on this rank's staged columns."""
+
+    def __init__(self, staging, col0):
+        self.staging, self.ncol, self.col0 = staging, staging.ncol, col0
+        self.tend = torch.zeros((staging.ncol, 7, NLEV), dtype=torch.float64)
+
+    def step_device(self, dt, f_les, f_gcm):
+        zf, zh = synth.les_grid(NK, 200.0)
+        gcm = {k: v.numpy() for k, v in self.staging.dev.items()}
+        aux = synth.make_les_aux(self.ncol, NK, seed=5, col0=self.col0, ncol_total=NCOL)
+        ref = synth.make_gcm_columns(self.ncol, NLEV, seed=5, col0=self.col0, ncol_total=NCOL)
+        vols = synth.make_les_volumes(ref, zf, NX, NX, seed=5, dtype=np.float32, col0=self.col0)
+        r = nb.coupling_step(gcm, zf, zh, vols, aux, aux["PS"], dt, f_les, f_gcm, True)
+        self.tend.copy_(torch.from_numpy(np.stack([r["tendencies"][k] for k in TENDENCIES], axis=1)))
+        return r["forcings"]
+
+
+def _exchange_worker(rank, world, port, outdir):
+    from sp_coupler_b200.pipeline import GcmStaging, HostExchange
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ncol = NCOL // world
+    st = GcmStaging(ncol, NLEV, torch.float64, "cpu", pin=False)
+    ex = HostExchange(st, world, rank, owner=0, register=False, tag="cputest", timeout_s=120.0)
+    pipe = _OraclePipe(st, rank * ncol)
+    full = synth.make_gcm_columns(NCOL, NLEV, seed=5)
+    for it in range(2):
+        if rank == 0:
+            g = dict(full)
+            if it == 1:
+                g["T"] = full["T"] + 1.5          # the host GCM moved on: every rank must see the new profiles
+            ex.fill_inputs(g)
+        _, out = ex.step(pipe, 900.0, 1.0, 1.0)
+        if rank == 0:
+            np.save(os.path.join(outdir, "out%d.npy" % it), out.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_host_exchange_shared_buffer(tmp_path):
+    """Sharded host-to-host step: the GCM owner publishes every rank's inputs in one shared host buffer, each rank
+    stages its own block, computes, and writes its own tendency block back; the owner ends up with all columns."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    zf, zh = synth.les_grid(NK, 200.0)
+    full = synth.make_gcm_columns(NCOL, NLEV, seed=5)
+    aux = synth.make_les_aux(NCOL, NK, seed=5)
+    vols = synth.make_les_volumes(full, zf, NX, NX, seed=5, dtype=np.float32)
+    for it in range(2):
+        g = dict(full)
+        if it == 1:
+            g["T"] = full["T"] + 1.5
+        r = nb.coupling_step(g, zf, zh, vols, aux, aux["PS"], 900.0, 1.0, 1.0, True)
+        want = np.stack([r["tendencies"][k] for k in TENDENCIES], axis=1)
+        assert np.array_equal(np.load(str(tmp_path / ("out%d.npy" % it))), want), it

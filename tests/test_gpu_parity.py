@@ -63,6 +63,8 @@ def check_step(case, ref, slab, frc, tnd, rtol, mask_expected=True):
     (2, 24, 20, 16, 19, np.float64),      # ragged float64 chunks
     (2, 48, 48, 40, 91, np.float32),      # three 4 KB sub-blocks per slab: 24 mask vectors per level (not a divisor of 32)
     (2, 32, 16, 160, 137, np.float32),    # 2 KB slabs: one partial sub-block, 8 mask vectors per level, four levels per warp pass
+    (1, 32, 32, 21, 19, np.float32),      # 4 KB slabs, odd slab count per field: one slab per copy instead of pairs
+    (5, 32, 16, 24, 19, np.float64),      # 4 KB float64 slabs in pairs
 ])
 def test_coupling_step_matches_oracle(cpl, cuda_device, ncol, nx, ny, nk, nlev, dtype):
     case = cases.host_case(ncol, nx, ny, nk, nlev, dtype)
