@@ -140,20 +140,36 @@ class HostExchange(object):
         self._off_in = self._off_out + al(nout)
         self.nbytes = self._off_in + al(nin)
         path = "/dev/shm/spcpl_b200_%s_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "r"), tag)
+        # every phase ends in an all_reduce(MIN) of "it worked here", so that all ranks either get the buffer or raise
+        # together - a rank that fails alone must never leave the others waiting in a collective
+        err = None
+        try:
+            if rank == owner:
+                with open(path, "wb") as f:
+                    f.truncate(self.nbytes)
+        except Exception as e:          # noqa: BLE001
+            err = e
+        ok = self._agree(err is None, group)
+        self.raw, self.registered = None, False
+        if ok:
+            try:
+                self.raw = torch.from_file(path, shared=True, size=self.nbytes, dtype=torch.uint8)
+                if register and torch.cuda.is_available():
+                    rc = torch.cuda.cudart().cudaHostRegister(self.raw.data_ptr(), self.nbytes, 0)
+                    if int(rc) != 0:
+                        raise RuntimeError("cudaHostRegister failed (%s)" % (rc,))
+                    self.registered = True
+            except Exception as e:      # noqa: BLE001
+                err = e
+            ok = self._agree(err is None, group)
         if rank == owner:
-            with open(path, "wb") as f:
-                f.truncate(self.nbytes)
-        torch.distributed.barrier(group=group)
-        self.raw = torch.from_file(path, shared=True, size=self.nbytes, dtype=torch.uint8)
-        torch.distributed.barrier(group=group)
-        if rank == owner:
-            os.unlink(path)            # the mapping stays alive in every process; nothing is left behind
-        self.registered = False
-        if register and torch.cuda.is_available():
-            rc = torch.cuda.cudart().cudaHostRegister(self.raw.data_ptr(), self.nbytes, 0)
-            if int(rc) != 0:
-                raise RuntimeError("cudaHostRegister of the shared host buffer failed (%s)" % (rc,))
-            self.registered = True
+            try:
+                os.unlink(path)        # the mapping stays alive in every process; nothing is left behind
+            except OSError:
+                pass
+        if not ok:
+            self.close()
+            raise RuntimeError("HostExchange: shared pinned host buffer unavailable on at least one rank (%s)" % (err,))
         self.flags = self.raw[:self.FLAG_WORDS * 8].view(torch.int64)          # [0] inputs ready, [1+r] rank r done
         self.out = self.raw[self._off_out:self._off_out + nout].view(dtype).view(world * ncol, 7, nlev)
         self.inp = self.raw[self._off_in:self._off_in + nin].view(dtype).view(world, self.per_rank_in)
@@ -161,6 +177,13 @@ class HostExchange(object):
             self.flags.zero_()
         torch.distributed.barrier(group=group)
         self.step_no = 0
+
+    @staticmethod
+    def _agree(ok, group):
+        dev = "cuda" if torch.distributed.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor([1 if ok else 0], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=group)
+        return bool(int(t.item()))
 
     def close(self):
         if self.registered:

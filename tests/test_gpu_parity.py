@@ -108,6 +108,7 @@ def test_ijk_layout_matches_oracle(cpl, cuda_device, dtype, shape):
     (2, 8, 8, 256, 19),      # two / four slots
     (2, 64, 64, 160, 91),    # C3 column shape
     (1, 4, 1, 160, 19),      # a single period per item: eleven warps have nothing to do
+    (1, 256, 256, 32, 19),   # C4 slab size: 65536 points per item, 1024 chunks per item
 ])
 def test_ijk_tma_path_matches_oracle(cpl, cuda_device, dtype, shape):
     """IJK shapes that take the per-warp TMA ring kernel (whole 16-byte vectors per point, period of at most
