@@ -212,6 +212,11 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        if args.bind:
+            from sp_coupler_b200.pipeline import bind_host_thread_to_gpu
+            cpus = bind_host_thread_to_gpu(dev)     # host pages and PCIe copies on the GPU's NUMA node
+            sys.stderr.write("rank %d: %s\n" % (rank, "bound to %d CPUs local to GPU %d (%d-%d)" % (len(cpus), local, cpus[0], cpus[-1])
+                                                 if cpus else "CPU binding unavailable"))
 
     ncol, nx, ny, nk, nlev, dts = CONFIGS[args.config]
     if args.ncol:
@@ -440,6 +445,7 @@ def main():
     ap.add_argument("--ref-reps", type=int, default=8, help="passes over them per step")
     ap.add_argument("--layout", default="kji", choices=["kji", "ijk"],
                     help="memory order of the LES volumes: kji = [ncol][nk][ny][nx] (DALES), ijk = [ncol][nx][ny][nk] (OMUSE view)")
+    ap.add_argument("--no-bind", dest="bind", action="store_false", help="N>1: do not bind rank processes to their GPU's CPUs")
     ap.add_argument("--no-host-exchange", dest="host_exchange", action="store_false",
                     help="N>1: time e2e through the owner GPU (device gather + one D2H) instead of the shared pinned host buffer")
     ap.add_argument("--no-graph", dest="graph", action="store_false",

@@ -109,6 +109,27 @@ class GcmScatter(object):
         return self.staging.dev
 
 
+def bind_host_thread_to_gpu(device):
+    """Restricts this process to the CPUs NVML reports as local to `device` (its NUMA node), so that the pinned host
+    pages it first touches and its PCIe copies stay on the GPU's side of the socket interconnect. Returns the CPU
+    list, or None when NVML / the affinity call is unavailable (then nothing changes)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(device)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08X:%02X:%02X.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)).encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:          # noqa: BLE001 - an optimisation only
+        return None
+
+
 class HostExchange(object):
     """Host side of a sharded step when the GCM lives in HOST memory of one process (OpenIFS does): one pinned
     host buffer shared by all ranks of the node (a /dev/shm mapping that every rank registers with CUDA).
@@ -154,6 +175,9 @@ class HostExchange(object):
         if ok:
             try:
                 self.raw = torch.from_file(path, shared=True, size=self.nbytes, dtype=torch.uint8)
+                # first touch: this rank's input and output blocks are allocated on the NUMA node it runs on
+                self.raw[self._off_in + rank * self.per_rank_in * esize:self._off_in + (rank + 1) * self.per_rank_in * esize].zero_()
+                self.raw[self._off_out + rank * self.per_rank_out * esize:self._off_out + (rank + 1) * self.per_rank_out * esize].zero_()
                 if register and torch.cuda.is_available():
                     rc = torch.cuda.cudart().cudaHostRegister(self.raw.data_ptr(), self.nbytes, 0)
                     if int(rc) != 0:
