@@ -178,6 +178,17 @@ int spc_searchsorted(spc_handle h, int dtype, const void* a, const void* v, int 
                      int nb, int na, int nv, int side_right, int32_t* out, void* stream);
 /* sputils.exner / iexner (sputils.py:28-34): out[i] = (p[i]/pref0)^(+-rd/cp) */
 int spc_exner(spc_handle h, int dtype, const void* p, size_t n, int inverse, void* out, void* stream);
+/* sputils.integral / interp_c / interp_rho (sputils.py:94-197): integrals of a piecewise-constant profile
+ * (q[nb][nq] on the cells [z[i], z[i+1]] of the ascending float64 edges z[nz], nq >= nz-1) over the layers
+ * [Zh[i+1], Zh[i]] of the descending edges Zh[nb][nlev+1]; out[nb][nlev]. mode:
+ *   SPC_INT_C       interp_c  : integral(q*w) / integral(w) where Zh[i] < z[nz-1], else 0 (sputils.py:173-189)
+ *   SPC_INT_RHO     interp_rho: integral(w) / (Zh[i] - Zh[i+1])  where Zh[i] < z[nz-1], else 0 (:191-197; q unused)
+ *   SPC_INT_PLAIN   integral(a=Zh[i+1], b=Zh[i], z, q)            (sputils.py:141-148, w == NULL)
+ *   SPC_INT_WEIGHTED integral(a, b, z, q, w)                      (sputils.py:150-161)
+ * The last two apply no range test: the caller keeps a and b inside [z[0], z[nz-1]] as the reference requires. */
+enum { SPC_INT_C = 0, SPC_INT_RHO = 1, SPC_INT_PLAIN = 2, SPC_INT_WEIGHTED = 3 };
+int spc_interp_c(spc_handle h, int dtype, const void* Zh, const double* z, int nz, const void* q, const void* w,
+                 int nq, int nb, int nlev, int mode, void* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * spcpl.set_les_state (spcpl.py:274-294): broadcast a vertical profile to a volume with uniform

@@ -4,6 +4,8 @@
 Run in the build container only (`python -m oracle.make_golden`); the fixtures are committed,
 so neither the CPU tests nor the GPU box need /root/reference.
 """
+import contextlib
+import io
 import os
 import sys
 import numpy as np
@@ -68,8 +70,40 @@ def make_nudge_golden():
         print(name, "-> beta", np.round(r["beta"], 3))
 
 
+def make_sputils_golden():
+    """sputils.integral / interp_c / interp_rho of the UNMODIFIED reference (sputils.py:94-197) on GCM layer edges
+    (descending) over the LES cells, with nk+1 edges (the documented call) and with nk edges (what spcpl.py:479-488
+    actually passes: zh_cache has nk entries)."""
+    sputils, _, _, _ = ref_driver.load_reference()
+    from omuse.units import units
+    blob = {}
+    for tag, nlev, nk, seed in (("a", 19, 20, 3), ("b", 91, 160, 4)):
+        dz = 25.0 if nk == 160 else 200.0
+        zf, zh = synth.les_grid(nk, dz)
+        gcm = synth.make_gcm_columns(2, nlev, seed=seed)
+        Zh = (gcm["Zghalf"] - gcm["Zghalf"][:, -1:]) / 9.81
+        rng = np.random.default_rng(seed)
+        q = 0.01 * np.exp(-zf / 2000.0)[None, :] * (1 + 0.1 * rng.normal(size=(2, nk)))
+        rho = 1.2 * np.exp(-zf / 8000.0)[None, :] * (1 + 0.01 * rng.normal(size=(2, nk)))
+        edges = np.append(zh, zh[-1] + dz)                               # nk+1 edges
+        for name, z in (("full", edges), ("short", zh)):
+            with contextlib.redirect_stdout(io.StringIO()):              # the len(z) != len(q)+1 message of :111-112
+                Qc = np.stack([np.asarray(sputils.interp_c(Zh[c] | units.m, z | units.m, q[c] | units.mfu, rho[c] | units.kg))
+                               for c in range(2)])
+                Rc = np.stack([np.asarray(sputils.interp_rho(Zh[c] | units.m, z | units.m, rho[c] | units.kg))
+                               for c in range(2)])
+            blob.update({"%s_%s_z" % (tag, name): z, "%s_%s_interp_c" % (tag, name): Qc, "%s_%s_interp_rho" % (tag, name): Rc})
+        ab = np.array([[30.0, 410.0], [410.0, 30.0], [0.0, float(zh[-1])], [125.0, 125.0], [12.5, 37.5]])
+        I = np.array([[float(sputils.integral(a, b, edges, q[0])), float(sputils.integral(a, b, edges, q[0], rho[0]))]
+                      for a, b in ab[:3]] + [[float(sputils.integral(a, b, edges, q[0])), np.nan] for a, b in ab[3:]])
+        blob.update({tag + "_Zh": Zh, tag + "_q": q, tag + "_rho": rho, tag + "_ab": ab, tag + "_integral": I})
+    np.savez_compressed(os.path.join(GOLDEN, "ref_sputils.npz"), **blob)
+    print("ref_sputils ->", len(blob), "arrays")
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    make_sputils_golden()
     make_nudge_golden()
     for name, ncol, nlev, nk, seed, dt, fl, fg, cons in CASES:
         zf, zh, gcm, aux, lp, A = case_inputs(ncol, nlev, nk, seed)

@@ -14,7 +14,7 @@ NFIELDS, NTEND = 5, 7
 
 # every symbol include/spcpl_b200.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = ["spc_abi_version", "spc_last_error", "spc_create", "spc_destroy", "spc_mask_words_per_column",
-           "spc_slab_reduce", "spc_gcm_to_les", "spc_les_to_gcm", "spc_cloud_fraction", "spc_interp", "spc_searchsorted", "spc_exner",
+           "spc_slab_reduce", "spc_gcm_to_les", "spc_les_to_gcm", "spc_cloud_fraction", "spc_interp", "spc_searchsorted", "spc_exner", "spc_interp_c",
            "spc_set_les_state", "spc_variability_nudge"]
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -79,6 +79,7 @@ def lib():
     L.spc_interp.argtypes = [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]
     L.spc_searchsorted.argtypes = [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]
     L.spc_exner.argtypes = [_vp, _i, _vp, C.c_size_t, _i, _vp, _vp]
+    L.spc_interp_c.argtypes = [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]
     L.spc_set_les_state.argtypes = [_vp, _vp, _d, C.c_uint32, C.c_uint32, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]
     L.spc_variability_nudge.argtypes = [_vp, C.POINTER(NudgeIO), _i, _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp]
     for name in SYMBOLS:

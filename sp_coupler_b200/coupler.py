@@ -292,6 +292,29 @@ class Coupler(object):
         self.launches += 1
         return out
 
+    INT_C, INT_RHO, INT_PLAIN, INT_WEIGHTED = 0, 1, 2, 3
+
+    def interp_c(self, Zh, z, q=None, w=None, mode=0):
+        """sputils.interp_c / interp_rho / integral over a batch of columns (sputils.py:94-197).
+        Zh [nb,nlev+1] descending layer edges; z [nz] float64 ascending cell edges; q, w [nb,nq>=nz-1] cell values.
+        mode: INT_C (mass-weighted mean per layer, 0 above z[-1]), INT_RHO (layer-mean of w), INT_PLAIN (integral of q),
+        INT_WEIGHTED (integral(q w)/integral(w) without the range rule). Returns [nb,nlev]."""
+        nb, nl1 = Zh.shape
+        dtype = Zh.dtype
+        self._chk(Zh, "Zh", dtype)
+        nz = z.shape[0]
+        self._chk(z, "z", torch.float64, (nz,))
+        ref = q if q is not None else w
+        nq = ref.shape[1]
+        for t, name in ((q, "q"), (w, "w")):
+            if t is not None:
+                self._chk(t, name, dtype, (nb, nq))
+        out = self._empty((nb, nl1 - 1), dtype)
+        _abi.check(self._lib.spc_interp_c(self._h, _DT[dtype], _ptr(Zh), _ptr(z), nz, _ptr(q), _ptr(w), nq, nb, nl1 - 1,
+                                          int(mode), _ptr(out), self._stream()), "spc_interp_c")
+        self.launches += 1
+        return out
+
     # ------------------------------------------------------------------ set_les_state
     def set_les_state(self, prof, amp, stream_id, nx, ny, seed=42, col0=0, sub=None, clamp0=False,
                       dtype=torch.float32, out=None):

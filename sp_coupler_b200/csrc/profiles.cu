@@ -610,6 +610,50 @@ __global__ void searchsorted_kernel(const T* a, const T* v, int v_batched, int n
   }
 }
 
+// sputils.integral without weights (sputils.py:141-148)
+__device__ double integral_plain(double a, double b, const double* z, int n, const double* q) {
+  int ia = 0;
+  while (ia + 1 < n - 1 && z[ia + 1] < a) ++ia;
+  int ib = ia;
+  while (ib + 1 < n - 1 && z[ib + 1] < b) ++ib;
+  double S = 0.0;
+  for (int i = ia; i <= ib; ++i) S += q[i] * (z[i + 1] - z[i]);        // sputils.py:142
+  return S - q[ia] * (a - z[ia]) - q[ib] * (z[ib + 1] - b);             // sputils.py:145-148
+}
+
+// sputils.interp_c / interp_rho / integral over a batch of columns: one block per column, one thread per layer,
+// the column's cell values staged in shared memory as float64.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) interp_c_kernel(const T* Zh, const double* z, int nz, const T* q, const T* w, int nq,
+                                                            int nlev, int mode, T* out) {
+  extern __shared__ __align__(16) double sm[];
+  double* zs = sm;             // [nz]
+  double* qs = zs + nz;        // [nz-1]
+  double* ws = qs + (nz - 1);  // [nz-1]
+  const int bidx = blockIdx.x;
+  for (int i = threadIdx.x; i < nz; i += blockDim.x) zs[i] = __ldg(z + i);
+  for (int i = threadIdx.x; i < nz - 1; i += blockDim.x) {
+    qs[i] = q ? (double)q[(size_t)bidx * nq + i] : 0.0;
+    ws[i] = w ? (double)w[(size_t)bidx * nq + i] : 1.0;
+  }
+  __syncthreads();
+  const T* Z = Zh + (size_t)bidx * (nlev + 1);
+  for (int l = threadIdx.x; l < nlev; l += blockDim.x) {
+    const double hi = (double)Z[l], lo = (double)Z[l + 1];
+    double r = 0.0;
+    if (mode == SPC_INT_C) {
+      if (hi < zs[nz - 1]) r = integral_w(lo, hi, zs, nz, qs, ws);                    // sputils.py:187-188
+    } else if (mode == SPC_INT_RHO) {
+      if (hi < zs[nz - 1]) r = integral_plain(lo, hi, zs, nz, ws) / (hi - lo);         // sputils.py:195-196
+    } else if (mode == SPC_INT_PLAIN) {
+      r = integral_plain(lo, hi, zs, nz, qs);
+    } else {
+      r = integral_w(lo, hi, zs, nz, qs, ws);
+    }
+    out[(size_t)bidx * nlev + l] = (T)r;
+  }
+}
+
 template <typename T>
 __global__ void exner_kernel(const T* p, size_t n, double e, T* out) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -774,6 +818,33 @@ int spc_searchsorted(spc_handle h, int dtype, const void* a, const void* v, int 
   else
     searchsorted_kernel<double><<<nb, kThreads, smem, st>>>((const double*)a, (const double*)v, v_batched, na, nv, side_right,
                                                            out);
+  SPC_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int spc_interp_c(spc_handle h, int dtype, const void* Zh, const double* z, int nz, const void* q, const void* w, int nq,
+                 int nb, int nlev, int mode, void* out, void* stream) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  SPC_REQUIRE(dtype == SPC_F32 || dtype == SPC_F64, SPC_ERR_ARG, "spc_interp_c: bad dtype %d", dtype);
+  SPC_REQUIRE(mode >= SPC_INT_C && mode <= SPC_INT_WEIGHTED, SPC_ERR_ARG, "spc_interp_c: bad mode %d", mode);
+  SPC_REQUIRE(nb >= 0 && nlev >= 0 && nz >= 2 && nq >= nz - 1, SPC_ERR_ARG, "spc_interp_c: bad shape nb=%d nlev=%d nz=%d nq=%d",
+              nb, nlev, nz, nq);
+  if (nb == 0 || nlev == 0) return SPC_OK;
+  SPC_REQUIRE(Zh && z && out, SPC_ERR_ARG, "spc_interp_c: NULL pointer");
+  SPC_REQUIRE(mode == SPC_INT_RHO || q, SPC_ERR_ARG, "spc_interp_c: q is NULL");
+  SPC_REQUIRE(mode == SPC_INT_PLAIN || w, SPC_ERR_ARG, "spc_interp_c: this mode needs the weights w");
+  const size_t smem = ((size_t)nz + 2 * (size_t)(nz - 1)) * sizeof(double);
+  SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_interp_c: nz=%d too large", nz);
+  spc::DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = column_threads(0, nlev);
+  if (dtype == SPC_F32)
+    interp_c_kernel<float><<<nb, threads, smem, st>>>((const float*)Zh, z, nz, (const float*)q, (const float*)w, nq, nlev, mode,
+                                                      (float*)out);
+  else
+    interp_c_kernel<double><<<nb, threads, smem, st>>>((const double*)Zh, z, nz, (const double*)q, (const double*)w, nq, nlev,
+                                                       mode, (double*)out);
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
 }

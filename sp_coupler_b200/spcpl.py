@@ -158,6 +158,28 @@ def convert_profiles(les, write=True):
     return d["u"][0], d["v"][0], d["thl"][0], d["qt"][0], d["ps"][0], d["ql_ref"][0]
 
 
+def output_column_conversion(profile):
+    """spcpl.py:251-270: derived diagnostics of one extra output column (no LES attached), in place:
+    Tv, Zh (without the top edge), Zf, Psurf, Ph (without the top edge), THL, QT from the GCM profiles
+    T, SH, QL, QI, Pf, Ph, Zgfull, Zghalf (1-D device tensors, top -> bottom). Same kernel as convert_profiles."""
+    T = profile['T']
+    cpl = default_coupler(T.device)
+    row = lambda t: t.reshape(1, -1).to(T.dtype).contiguous()
+    zero = torch.zeros_like(T)
+    g = {"U": row(profile.get('U', zero)), "V": row(profile.get('V', zero)), "T": row(T), "SH": row(profile['SH']),
+         "QL": row(profile['QL']), "QI": row(profile['QI']), "Pfull": row(profile['Pf']), "A": row(profile.get('A', zero)),
+         "Zgfull": row(profile['Zgfull']), "Phalf": row(profile['Ph']), "Zghalf": row(profile['Zghalf'])}
+    d = cpl.gcm_to_les(g, torch.zeros(1, dtype=torch.float64, device=T.device), None, None, None, 1.0, 1.0, False,
+                       diagnostics=True)
+    profile['Tv'] = d["Tv"][0]                                                           # spcpl.py:253
+    profile['Zh'] = d["Zh"][0][1:]                                                       # spcpl.py:258,261
+    profile['Zf'] = d["Zf"][0]                                                           # spcpl.py:259,262
+    profile['Psurf'] = profile['Ph'][-1]                                                 # spcpl.py:263
+    profile['Ph'] = profile['Ph'][1:]                                                    # spcpl.py:264
+    profile['THL'] = d["THL"][0]                                                         # spcpl.py:265-266
+    profile['QT'] = d["QT"][0]                                                           # spcpl.py:267
+
+
 def set_les_state(les, u, v, thl, qt, ps=None):
     """spcpl.py:274-294: broadcast the profiles to the 3-D fields with uniform noise of amplitude
     0.5 m/s, 0.1 K, 2.5e-5 (Philox stream instead of numpy's Mersenne Twister)."""

@@ -135,3 +135,53 @@ def test_set_les_state_and_diagnostics_store(world, cuda_device):
                  "u", "v", "presf", "rhof", "rhobf", "qt", "ql", "ql_ice", "ql_water", "thl", "t", "t_", "qr",
                  "f_U", "f_V", "f_T", "f_SH", "A", "A_d", "f_QL", "f_QI", "f_A"):
         assert want in names, want
+
+
+def test_sputils_integrals_match_reference_golden(cuda_device):
+    """sputils.integral / interp_c / interp_rho on the GPU path against the unmodified reference's outputs."""
+    import os
+    import torch
+    from conftest import GOLDEN, relerr
+    from sp_coupler_b200 import sputils
+    z = np.load(os.path.join(GOLDEN, "ref_sputils.npz"))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    for tag in ("a", "b"):
+        Zh, q, rho = t(z[tag + "_Zh"]), t(z[tag + "_q"]), t(z[tag + "_rho"])
+        for name in ("full", "short"):
+            edges = t(z["%s_%s_z" % (tag, name)])
+            qc = sputils.interp_c(Zh, edges, q, rho)                        # batched over the two columns
+            assert relerr(qc.cpu().numpy(), z["%s_%s_interp_c" % (tag, name)]) <= 1e-13
+            rc = sputils.interp_rho(Zh[1], edges, rho[1])                   # one column, reference call shape
+            assert relerr(rc.cpu().numpy(), z["%s_%s_interp_rho" % (tag, name)][1]) <= 1e-13
+            zero = z["%s_%s_interp_c" % (tag, name)] == 0                   # layers above the LES top stay exactly 0
+            assert zero.any() and (qc.cpu().numpy()[zero] == 0).all()
+        edges = t(z[tag + "_full_z"])
+        scale = float(np.abs(z[tag + "_integral"][2, 0]))
+        for (a, b), (plain, weighted) in zip(z[tag + "_ab"], z[tag + "_integral"]):
+            assert abs(float(sputils.integral(a, b, edges, q[0])) - plain) <= 1e-13 * scale
+            if not np.isnan(weighted):
+                assert abs(float(sputils.integral(a, b, edges, q[0], rho[0])) - weighted) <= 1e-13 * abs(weighted)
+        assert sputils.integral(-1.0, 10.0, edges, q[0]) is None
+    f32 = sputils.interp_c(Zh.float(), edges, q.float(), rho.float())        # float32 storage, float64 arithmetic
+    assert relerr(f32.cpu().numpy(), z["b_full_interp_c"]) <= 1e-6
+
+
+def test_output_column_conversion(cuda_device):
+    """spcpl.output_column_conversion (spcpl.py:251-270) against the same expressions in numpy."""
+    import torch
+    from sp_coupler_b200 import spcpl, synth
+    from oracle import numpy_batched as nb
+    g = synth.make_gcm_columns(1, 91, seed=12)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[0])).to(cuda_device)
+    prof = {"T": t(g["T"]), "SH": t(g["SH"]), "QL": t(g["QL"]), "QI": t(g["QI"]), "Pf": t(g["Pfull"]), "Ph": t(g["Phalf"]),
+            "Zgfull": t(g["Zgfull"]), "Zghalf": t(g["Zghalf"])}
+    spcpl.output_column_conversion(prof)
+    T, SH, QL, QI = g["T"][0], g["SH"][0], g["QL"][0], g["QI"][0]
+    c = nb.rv / nb.rd - 1
+    want = {"Tv": T * (1 + c * SH - (QL + QI)), "Zh": ((g["Zghalf"][0] - g["Zghalf"][0][-1]) / nb.grav)[1:],
+            "Zf": (g["Zgfull"][0] - g["Zghalf"][0][-1]) / nb.grav, "Psurf": g["Phalf"][0][-1], "Ph": g["Phalf"][0][1:],
+            "THL": (T - (nb.rlv * (QL + QI)) / nb.cp) * nb.iexner(g["Pfull"][0]), "QT": SH + QL + QI}
+    for k, v in want.items():
+        got = prof[k].cpu().numpy()
+        assert got.shape == np.shape(v), k
+        assert np.max(np.abs(got - v)) <= 1e-12 * np.max(np.abs(v)), k

@@ -1,10 +1,12 @@
 """Pins oracle/numpy_batched.py: against the reference's own known-answer tests, against golden
 vectors produced by the unmodified reference (tests/golden/, oracle/make_golden.py), and — where
 /root/reference is present — against the reference run live."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, load_golden, relerr
+from conftest import GOLDEN, GOLDEN_CASES, load_golden, relerr
 from oracle import numpy_batched as nb
 from oracle import ref_driver
 
@@ -154,3 +156,23 @@ def test_oracle_matches_reference_live():
     for k in TEND_KEYS:
         assert relerr(t[k], r[k]) <= 1e-13, k
     assert np.array_equal(t["start_index"], r["start_index"])
+
+
+def test_oracle_integrals_match_reference_golden():
+    """sputils.integral / interp_c / interp_rho (sputils.py:94-197): the restatement against outputs of the unmodified
+    reference (tests/golden/ref_sputils.npz, oracle/make_golden.py), with nk+1 cell edges and with the nk edges the
+    coupler actually passes."""
+    z = np.load(os.path.join(GOLDEN, "ref_sputils.npz"))
+    for tag in ("a", "b"):
+        Zh, q, rho = z[tag + "_Zh"], z[tag + "_q"], z[tag + "_rho"]
+        for name in ("full", "short"):
+            edges = z["%s_%s_z" % (tag, name)]
+            for c in range(2):
+                assert np.array_equal(nb.interp_c(Zh[c], edges, q[c], rho[c]), z["%s_%s_interp_c" % (tag, name)][c])
+                assert np.array_equal(nb.interp_rho(Zh[c], edges, rho[c]), z["%s_%s_interp_rho" % (tag, name)][c])
+        edges = z[tag + "_full_z"]
+        for (a, b), (plain, weighted) in zip(z[tag + "_ab"], z[tag + "_integral"]):
+            assert nb.integral_plain(a, b, edges, q[0]) == plain
+            if not np.isnan(weighted):
+                assert nb.integral(a, b, edges, q[0], rho[0]) == weighted
+        assert nb.integral_plain(-1.0, 10.0, edges, q[0]) is None          # end point outside the range: sputils.py:113-115
