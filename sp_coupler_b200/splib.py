@@ -34,6 +34,7 @@ max_num_les = -1
 les_forcing_factor = 1.0
 gcm_forcing_factor = 1.0
 les_spinup = 0
+les_spinup_steps = 1
 les_spinup_forcing_factor = 1.0
 cplsurf = False
 qt_forcing = "sp"
@@ -116,6 +117,8 @@ def initialize(config=None, geometries=None, output_geometries=None, device=None
     les_batch.initialize_state(d)                                                 # set_les_state,    splib.py:204
     les_batch.aux["PS"].copy_(d["ps"])
     firststep, profiles, timing_rows = True, {}, []
+    if les_spinup > 0:                                                            # splib.py:206-207
+        run_spinup(les_spinup, les_spinup_steps)
     return les_models
 
 
@@ -127,10 +130,11 @@ def _gather(couple_surface):
         spcpl.gather_gcm_data(gcm_model, les_models, couple_surface, None, write=write_diagnostics)
 
 
-def step_les_models(model_time):
-    """splib.py:554-617: advance every LES to model_time, then fetch its profiles."""
+def step_les_models(model_time, offset=None):
+    """splib.py:554-617: advance every LES to model_time (+ the spin-up offset of the LES clocks), then fetch
+    its profiles."""
     start = time.time()
-    les_batch.evolve(model_time)
+    les_batch.evolve(model_time + (les_spinup if offset is None else offset))
     if per_column:
         prof = {}
         for les in les_models:
@@ -199,6 +203,52 @@ def step():
         timing_file.flush()
     firststep = False
     return row
+
+
+def step_spinup(spinup_length):
+    """One spin-up iteration (splib.py:355-402): the LES are nudged towards the initial GCM profiles over
+    `spinup_length` seconds with `les_spinup_forcing_factor`; the GCM does not step and gets no tendencies.
+    Same kernels as a coupled step: K2 with dt = spinup_length, LES stand-in, K1 (the profiles feed the next
+    iteration's forcings and the diagnostics store)."""
+    global firststep, profiles
+    if not les_models:
+        return None
+    starttime = time.time()
+    t_les = les_batch.model_time
+    forc = -time.time()
+    if per_column:                                                                # splib.py:375-382
+        for les in les_models:
+            spcpl.set_les_forcings(les, gcm_model, True, firststep, profiles.get(les, {}), dt_gcm=spinup_length,
+                                   factor=les_spinup_forcing_factor, couple_surface=cplsurf, qt_forcing=qt_forcing,
+                                   write=write_diagnostics)
+    else:
+        spcpl.set_les_forcings_all(les_batch, spinup_length, les_spinup_forcing_factor, cplsurf, firststep)
+    torch.cuda.synchronize()
+    forc += time.time()
+    les_wall_times, profiles = step_les_models(t_les + spinup_length, offset=0)   # splib.py:386
+    tend = -time.time()                                                           # profile writing, splib.py:387-391
+    if write_diagnostics:
+        for les in les_models:
+            spcpl.write_les_profiles(les)
+    tend += time.time()
+    firststep = False
+    row = (starttime, 0.0, 0.0, forc, tend, 0.0)                                  # splib.py:396-400
+    timing_rows.append(row)
+    if timing_file:
+        timing_file.write(('%10.2f %6.2f %6.2f %6.2f %6.2f %6.2f' % row) + ' ' +
+                          ' '.join(['%6.2f' % w for w in les_wall_times[:8]]) + '\n')
+        timing_file.flush()
+    return row
+
+
+def run_spinup(spinup_length, spinup_steps=1):
+    """splib.py:233-251: `spinup_steps` iterations covering `spinup_length` seconds in total."""
+    iteration_length = spinup_length / spinup_steps
+    for s in range(spinup_steps):
+        if s == spinup_steps - 1:
+            iteration_length = spinup_length - (spinup_steps - 1) * iteration_length
+        step_spinup(iteration_length)
+    log.info('  ---- Spinup done ---')
 
 
 def open_timing_file(name="timing.txt"):

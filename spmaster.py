@@ -24,6 +24,9 @@ def main(argv=None):
     p.add_argument("--cplsurf", dest="cplsurf", action="store_true", help="couple surface fluxes")
     p.add_argument("--lesforcingfactor", dest="les_forcing_factor", type=float, default=1.0)
     p.add_argument("--gcmforcingfactor", dest="gcm_forcing_factor", type=float, default=1.0)
+    p.add_argument("--spinup", dest="les_spinup", type=float, default=0, help="time (s) of initial LES spin-up towards the initial profile")
+    p.add_argument("--spinup_steps", dest="les_spinup_steps", type=int, default=1, help="number of iterations of the spin-up nudging")
+    p.add_argument("--spinup_forcing", dest="les_spinup_forcing_factor", type=float, default=1.0, help="forcing strength during LES spin-up")
     p.add_argument("--qt_forcing", dest="qt_forcing", default="sp", choices=["sp", "variance"])
     p.add_argument("--conservative_coarsening", dest="conservative_coarsening", action="store_true")
     p.add_argument("--nx", dest="les_nx", type=int, default=64)

@@ -185,3 +185,30 @@ def test_output_column_conversion(cuda_device):
         got = prof[k].cpu().numpy()
         assert got.shape == np.shape(v), k
         assert np.max(np.abs(got - v)) <= 1e-12 * np.max(np.abs(v)), k
+
+
+def test_spinup_then_coupled_steps(cuda_device):
+    """splib.run_spinup / step_spinup (splib.py:233-251, 355-402): the LES relax towards the initial GCM profiles
+    with the spin-up forcing factor, the GCM neither steps nor receives tendencies; the coupled steps that follow
+    advance the LES clocks from the spin-up offset."""
+    import torch
+    from sp_coupler_b200 import splib
+    cfg = dict(max_num_les=4, les_nx=16, les_ny=16, les_nk=160, gcm_nlev=19, dtype="f64", cplsurf=True)
+    splib.initialize(dict(cfg, les_spinup=0), device=cuda_device)
+    b0 = splib.les_batch
+    thl0 = b0.vols[0].clone()
+    gcm_T0 = splib.gcm_model.state["T"].copy()
+    splib.initialize(dict(cfg, les_spinup=1800.0, les_spinup_steps=3, les_spinup_forcing_factor=0.5), device=cuda_device)
+    b = splib.les_batch
+    assert b.model_time == 1800.0 and len(splib.timing_rows) == 3
+    assert all(r[1] == 0.0 and r[2] == 0.0 and r[5] == 0.0 for r in splib.timing_rows)   # no GCM work in a spin-up row
+    assert np.array_equal(splib.gcm_model.state["T"], gcm_T0)                             # the GCM got no tendencies
+    # same initial state (seeded), then nudged: the slab means moved towards the GCM profile on the LES levels
+    target = b.cpl.gcm_to_les(b.pipe.gcm, b.pipe.zf, b.pipe.zh, None, None, 1.0, 1.0, False, want_state=True)["thl"].double()
+    before = (thl0.double().mean(dim=(2, 3)) - target).abs().mean()
+    after = (b.vols[0].double().mean(dim=(2, 3)) - target).abs().mean()
+    assert float(after) < float(before)
+    assert not splib.firststep
+    splib.step()
+    assert b.model_time == 1800.0 + splib.gcm_model.get_timestep()
+    splib.finalize()
