@@ -239,16 +239,20 @@ class HostExchange(object):
         self.step_no += 1
         self.flags[0] = self.step_no
 
-    def step(self, pipe, dt=900.0, f_les=1.0, f_gcm=1.0):
-        """One sharded host-to-host step (all ranks call it; the owner calls publish_inputs() first or passes
-        through here with inputs unchanged). Returns (forcings, out) - `out` is complete on the owner only."""
+    def fetch_inputs(self, pipe):
+        """All ranks, once per step (the owner after fill_inputs): wait for the step's inputs and stage this rank's
+        block on its device. Returns the rank's device views (pipe.staging.dev)."""
         if self.rank == self.owner:
             self.publish_inputs()
         else:
             self.step_no += 1
         self._wait(0, self.step_no)
         pipe.staging.dev_buf.copy_(self.inp[self.rank], non_blocking=True)
-        frc = pipe.step_device(dt, f_les, f_gcm)
+        return pipe.staging.dev
+
+    def put_tendencies(self, pipe):
+        """All ranks, once per step after K3: this rank's tendency block goes to its rows of the shared `out`; the
+        owner returns when every rank's block has landed (`out` is complete on the owner only)."""
         lo = self.rank * pipe.ncol
         self.out[lo:lo + pipe.ncol].copy_(pipe.tend, non_blocking=True)
         if pipe.tend.is_cuda:
@@ -257,7 +261,14 @@ class HostExchange(object):
         if self.rank == self.owner:
             for r in range(self.world):
                 self._wait(1 + r, self.step_no)
-        return frc, self.out
+        return self.out
+
+    def step(self, pipe, dt=900.0, f_les=1.0, f_gcm=1.0):
+        """One sharded host-to-host step (all ranks call it; the owner refreshes the inputs with fill_inputs()
+        beforehand when the GCM has moved on). Returns (forcings, out) - `out` is complete on the owner only."""
+        self.fetch_inputs(pipe)
+        frc = pipe.step_device(dt, f_les, f_gcm)
+        return frc, self.put_tendencies(pipe)
 
 
 class CouplingPipeline(object):

@@ -117,8 +117,26 @@ def gather_gcm_data_sharded(gcm, batch, couple_surface=True):
     owns the GCM fetches the profiles of ALL columns (spcpl.py:62-75), packs them per rank, uploads once,
     and a scatter over NVLink delivers every rank's block into its staging buffer; then the per-LES
     attributes are views of the device arrays as in the single-GPU path (spcpl.py:81-86)."""
-    from .pipeline import GcmScatter
+    from .pipeline import GcmScatter, HostExchange
     pipe = batch.pipe
+    if getattr(batch, "gather_mode", None) == "host":
+        # the GCM's host memory is one pinned buffer shared by all ranks: every rank stages its own columns over
+        # its own PCIe link (pipeline.HostExchange); the tendencies go back the same way (set_gcm_tendencies_all)
+        if getattr(batch, "_exchange", None) is None:
+            batch._exchange = HostExchange(pipe.staging, pipe.world, pipe.rank, owner=0, group=pipe.group, tag="splib")
+        if pipe.rank == 0:
+            cols = batch.all_grid_indices
+            data = {v: gcm.get_profile_fields(v, cols) for v in gcm_vars}
+            data.update({v: gcm.get_surface_field(v, cols) for v in surf_vars})
+            batch._exchange.fill_inputs(data)
+        dev = batch._exchange.fetch_inputs(pipe)
+        for i, les in enumerate(batch.models):
+            for v in gcm_vars:
+                setattr(les, v, dev[v][i])
+            if couple_surface:
+                for v in surf_vars:
+                    setattr(les, v, dev[v][i])
+        return dev
     if getattr(batch, "_scatter", None) is None:
         batch._scatter = GcmScatter(pipe.staging, pipe.world, pipe.rank, owner=0, group=pipe.group)
     if pipe.rank == 0:
@@ -341,6 +359,11 @@ def set_gcm_tendencies_all(gcm, batch, dt_gcm, factor=1, conservative=False, to_
     packed [ncol][7][nlev] block goes back to the host GCM in one copy."""
     pipe = batch.pipe
     res = pipe.tendencies(batch.last_forcings, float(dt_gcm), float(factor), conservative=conservative)
+    if getattr(batch, "_exchange", None) is not None:          # sharded, host-resident GCM: no device gather
+        out = batch._exchange.put_tendencies(pipe)
+        if to_host and gcm is not None and pipe.rank == 0:
+            gcm.set_profile_tendencies(batch.all_grid_indices, out)
+        return res
     if to_host and gcm is not None and pipe.rank == 0:
         pipe.tend_host.copy_(pipe.tend_all, non_blocking=True)
         torch.cuda.current_stream(pipe.cpl.device).synchronize()

@@ -165,8 +165,9 @@ class gpu_les_batch(object):
         self.ncol, self.nlev, self.nx, self.ny, self.nk, self.dtype = ncol, nlev, nx, ny, nk, dtype
         self.seed, self.col0 = seed, col0
         self.zf_host, self.zh_host = synth.les_grid(nk, dz)
+        self.gather_mode = gather                  # "host": no device gather, tendencies leave through pipeline.HostExchange
         self.pipe = CouplingPipeline(self.cpl, self.zf_host, self.zh_host, ncol, nlev, dtype, couple_surface,
-                                     group=group, gather=gather)
+                                     group=group, gather=False if gather == "host" else gather)
         dev = self.cpl.device
         self.vols = [torch.zeros((ncol, nk, ny, nx), dtype=dtype, device=dev) for _ in LES_FIELDS]
         ndt = np.float32 if dtype == torch.float32 else np.float64

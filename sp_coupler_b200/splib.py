@@ -46,7 +46,7 @@ les_nx, les_ny, les_nk, les_dz = 64, 64, 160, 25.0
 gcm_nlev = 91
 dtype = "f32"
 per_column = False          # True: drive the kernels through the per-LES reference-shaped calls
-gather_mode = "nccl"        # multi-GPU tendency gather: "nccl" | "p2p" | "p2p-owner" (pipeline.py)
+gather_mode = "nccl"        # multi-GPU tendency gather: "nccl" | "p2p" | "p2p-owner" | "host" (pipeline.py)
 write_diagnostics = False
 
 gcm_model = None

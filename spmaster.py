@@ -38,8 +38,9 @@ def main(argv=None):
                    help="drive the kernels through the per-LES reference-shaped calls")
     p.add_argument("--output", dest="output_name", default="spifs.npz")
     p.add_argument("--write", dest="write_diagnostics", action="store_true")
-    p.add_argument("--gather", dest="gather_mode", default="nccl", choices=["nccl", "p2p", "p2p-owner"],
-                   help="multi-GPU tendency gather (under torch.distributed.run)")
+    p.add_argument("--gather", dest="gather_mode", default="nccl", choices=["nccl", "p2p", "p2p-owner", "host"],
+                   help="multi-GPU tendency gather (under torch.distributed.run): NCCL all_gather, fused NVLink stores, "
+                        "or 'host' = every rank exchanges its own columns with the GCM through one shared pinned host buffer")
     p.add_argument("--save_state", default=None, help="write the final GCM state of the SP columns to this .npz")
     args = p.parse_args(argv)
 
