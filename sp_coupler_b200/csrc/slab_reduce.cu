@@ -809,10 +809,11 @@ int launch_tma(spc_handle h, const K1Args& a, cudaStream_t st) {
   return SPC_OK;
 }
 
-// Ring shapes. Production picks by slab size (round-1 sweep on B200, profiles/README.md): about
-// 96 KB in flight per SM in single-stage per-warp rings is the sweet spot - deeper rings (192 KB)
-// cost ~8 % of bandwidth, fewer than 8 warps cannot keep up with the float32->float64 conversions.
-//   slab >= 8 KB : 12 warps x 1 x 8 KB      slab < 8 KB : 24 warps x 1 x 4 KB
+// Ring shapes. Production picks by slab size and element type (round-1 sweeps on B200, profiles/README.md): with the
+// evict_normal L2 policy 96-128 KB in flight per SM in single-stage per-warp rings is the sweet spot - deeper rings
+// (192 KB) cost 6-8 % of bandwidth, fewer than 8 warps cannot keep up with the float32->float64 conversions.
+//   slab >= 8 KB : float32 16 warps x 1 x 8 KB, float64 12 warps x 1 x 8 KB
+//   slab  = 4 KB : pairs of slabs, 12 warps x 1 x 8 KB (slab_reduce_tma_pair_kernel)     other slab < 8 KB : 24 warps x 1 x 4 KB
 // Variants 1.. exist for tools/k1_probe.py (spc_tune_k1) and document the sweep.
 #define SPC_K1_VARIANTS(X)                                                               \
   X(1, 12, 8192, 1, false) X(2, 24, 4096, 1, false) X(3, 16, 4096, 3, false) X(4, 8, 8192, 2, false) \
@@ -820,11 +821,12 @@ int launch_tma(spc_handle h, const K1Args& a, cudaStream_t st) {
 // extra probes of the production shape: L2 policy of the copies (10 = evict_first, 12 = no cache hint, 14 = evict_last; production is
 // evict_normal: +0.7 % float32, +4.5 % float64, +1.9 % at 256 KB slabs over evict_first) and 11 = both sub-blocks of a chunk per trip
 #define SPC_K1_VARIANTS2(Y) Y(10, 12, 8192, 1, false, 0, 1) Y(11, 12, 8192, 1, false, 1, 2) Y(12, 12, 8192, 1, false, 2, 1) \
-  Y(14, 12, 8192, 1, false, 3, 1) Y(15, 24, 4096, 1, false, 0, 1)
+  Y(14, 12, 8192, 1, false, 3, 1) Y(15, 24, 4096, 1, false, 0, 1) \
+  Y(16, 8, 8192, 3, false, 1, 1) Y(17, 8, 8192, 2, false, 1, 2) Y(18, 8, 8192, 2, false, 2, 1) Y(19, 16, 8192, 1, false, 1, 1) \
+  Y(20, 8, 8192, 2, false, 0, 1) Y(21, 6, 16384, 2, false, 1, 1)
 
-template <typename T>
+template <typename T, int W>
 int launch_tma_pair(spc_handle h, const K1Args& a, cudaStream_t st) {
-  constexpr int W = 12;
   const size_t smem = (size_t)W * 2 * kSubBytes + (size_t)W * 8;
   static thread_local int configured_dev = -1;
   if (configured_dev != h->device) {
@@ -837,13 +839,14 @@ int launch_tma_pair(spc_handle h, const K1Args& a, cudaStream_t st) {
   return SPC_OK;
 }
 
-int k1_variant_for(int slab_bytes) {
+int k1_variant_for(int slab_bytes, int esize) {
   if (g_k1_variant != 0) return g_k1_variant;
-  return slab_bytes >= 8192 ? 1 : 2;
+  if (slab_bytes < 8192) return 2;
+  return esize == 4 ? 19 : 1;   // float32 needs more warps for the conversions: 16 x 1 x 8 KB; float64: 12 x 1 x 8 KB
 }
 
-int k1_chunk_bytes(int slab_bytes) {
-  switch (k1_variant_for(slab_bytes)) {
+int k1_chunk_bytes(int slab_bytes, int esize) {
+  switch (k1_variant_for(slab_bytes, esize)) {
 #define X(id, w, c, s, b) case id: return c;
     SPC_K1_VARIANTS(X)
 #undef X
@@ -856,12 +859,13 @@ int k1_chunk_bytes(int slab_bytes) {
 
 template <typename T>
 int launch_kji(spc_handle h, const K1Args& a, bool fast, cudaStream_t st) {
-  if (fast && a.slab_bytes == kSubBytes && a.per_field % 2 == 0 && (g_k1_variant == 0 || g_k1_variant == 9)) {
-    const int rc = launch_tma_pair<T>(h, a, st);   // 4 KB slabs in pairs (variant 9; 2 = one slab per copy)
+  if (fast && a.slab_bytes == kSubBytes && a.per_field % 2 == 0 && (g_k1_variant == 0 || g_k1_variant == 9 || g_k1_variant == 22)) {
+    // 4 KB slabs in pairs (variant 9 = 12 warps, 22 = 16 warps; 2 = one slab per copy)
+    const int rc = g_k1_variant == 22 ? launch_tma_pair<T, 16>(h, a, st) : launch_tma_pair<T, 12>(h, a, st);
     if (rc) return rc;
   } else if (fast) {
     int rc;
-    switch (k1_variant_for(a.slab_bytes)) {
+    switch (k1_variant_for(a.slab_bytes, (int)sizeof(T))) {
 #define X(id, w, c, s, b) case id: rc = launch_tma<T, Ring<w, c, s, b>>(h, a, st); break;
       SPC_K1_VARIANTS(X)
 #undef X
@@ -1016,7 +1020,8 @@ int spc_slab_reduce(spc_handle h, const void* const vol[5], int dtype, int layou
   a.total = a.per_field * SPC_NFIELDS;
   a.S = (int)S;
   a.slab_bytes = (int)(S * (dtype == SPC_F32 ? 4 : 8));
-  a.nch = (a.slab_bytes + k1_chunk_bytes(a.slab_bytes) - 1) / k1_chunk_bytes(a.slab_bytes);
+  const int chunk = k1_chunk_bytes(a.slab_bytes, dtype == SPC_F32 ? 4 : 8);
+  a.nch = (a.slab_bytes + chunk - 1) / chunk;
   a.nsub = (a.slab_bytes + kSubBytes - 1) / kSubBytes;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (layout == SPC_LAYOUT_IJK) {
