@@ -45,12 +45,35 @@ def test_sass_is_sm100a_with_tma_bulk():
     assert "LDS.128" in sass
 
 
-def test_struct_sizes_match_header():
+def test_struct_layouts_match_header_compiled_as_c(tmp_path):
+    """The header must be plain C (what a cgo / Fortran-C / ctypes-gen consumer compiles) and every field of the
+    ctypes mirror must sit at the offset gcc gives it."""
+    import shutil
+    import subprocess
     from sp_coupler_b200 import _abi
-    assert ctypes.sizeof(_abi.GcmCols) == 16 + 18 * 8        # 3 ints (+pad) + 18 pointers
-    assert ctypes.sizeof(_abi.LesForcing) == 23 * 8
-    assert ctypes.sizeof(_abi.LesProf) == 8 * 8 + 4 * 4
-    assert ctypes.sizeof(_abi.GcmTend) == 8 * 8 + 2 * 4
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    mirrors = {"spc_gcm_cols": _abi.GcmCols, "spc_les_forcing": _abi.LesForcing, "spc_les_prof": _abi.LesProf,
+               "spc_gcm_tend": _abi.GcmTend, "spc_nudge_io": _abi.NudgeIO}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "spcpl_b200.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append('  printf("%s.sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  printf("enum %d %d %d %d %d\\n", SPC_F64, SPC_LAYOUT_IJK, SPC_NFIELDS, SPC_NTEND, SPC_INT_WEIGHTED);',
+              '  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    out = dict(l.rsplit(" ", 1) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+               if not l.startswith("enum"))
+    for cname, cls in mirrors.items():
+        assert ctypes.sizeof(cls) == int(out[cname + ".sizeof"]), cname
+        for fname, _ in cls._fields_:
+            assert getattr(cls, fname).offset == int(out["%s.%s" % (cname, fname)]), (cname, fname)
+    assert (_abi.SPC_F64, _abi.LAYOUT_IJK, _abi.NFIELDS, _abi.NTEND) == (1, 1, 5, 7)
 
 
 def test_no_cpu_fallback():
