@@ -9,6 +9,13 @@
 // complete_tx). Lane 0 keeps the ring full; the warp reduces a landed chunk in 4 KB sub-blocks with
 // conflict-free 128-bit LDS, accumulating in float64 (so the mean is order-insensitive to ~1e-16),
 // and finishes a slab with a shuffle butterfly. No block-wide barriers, no atomics, fixed order.
+//
+// Kernels in this file
+//   slab_reduce_tma_kernel<T, Ring>        KJI, slabs >= 1 KB and a multiple of 16 bytes (the production path)
+//   slab_reduce_tma_pair_kernel<T, W>      KJI, 4 KB slabs: two slabs per 8 KB copy
+//   slab_reduce_generic_kernel<T>          KJI, any other slab size / alignment (one warp per slab, scalar loads)
+//   slab_reduce_ijk_tma_kernel<T, SLOTS>   IJK (k fastest), per-warp TMA rings over whole (field, column) items
+//   slab_reduce_ijk_kernel<T, VEC>         IJK, shapes outside the TMA plan (one CTA per item)
 #include <type_traits>
 
 #include "spc_common.cuh"
