@@ -7,7 +7,8 @@ legs may import this package; the product (sp_coupler_b200/) never does.
 
 Parity status
   * Profile math (convert_profiles, set_les_forcings, convert_surface_fluxes,
-    set_gcm_tendencies, cloud-fraction index mapping, exner/iexner): PINNED against
+    set_gcm_tendencies, cloud-fraction index mapping, exner/iexner, integral / interp_c /
+    interp_rho): PINNED against
     (a) the reference's own known-answer tests (splib/test/sputils_test.py:25-39,
     splib/test/spcpl_test.py:10-16) and (b) golden vectors produced by running the
     UNMODIFIED reference functions from /root/reference under oracle/stubs
@@ -16,7 +17,9 @@ Parity status
     external DALES worker (call sites spcpl.py:748-766); nothing under /root/reference
     computes them and no reference test pins them -> "parity unpinned" for these two.
     The contract is BASELINE.json's north_star: horizontal mean; cloud fraction = count of
-    ql > threshold.  Definitions are in slab_reduce() / cloud_project() below.
+    ql > threshold.  Definitions are in slab_reduce() / cloud_project() below. (The only
+    in-tree statement of a slab average, `.sum() / (itot * jtot)` over field[:, :, k] at
+    spcpl.py:642,650, is the same definition.)
 
 Orientation: GCM arrays run top -> bottom (index 0 = model top; half-level arrays have
 nlev+1 entries ending at the ground); LES arrays bottom -> top.
