@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _abi
-from .constants import LES_FIELDS, TENDENCIES, gcm_vars, surf_vars
+from .constants import LES_FIELDS, TENDENCIES, surf_vars
 
 _DT = {torch.float32: _abi.SPC_F32, torch.float64: _abi.SPC_F64}
 _LAYOUT = {"kji": _abi.LAYOUT_KJI, "ijk": _abi.LAYOUT_IJK, 0: 0, 1: 1}

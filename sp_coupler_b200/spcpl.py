@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import spio
-from .constants import LES_FIELDS, TENDENCIES, gcm_vars, surf_vars
+from .constants import LES_FIELDS, gcm_vars, surf_vars
 from .coupler import default_coupler
 
 log = logging.getLogger(__name__)

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import synth
-from .constants import LES_FIELDS, gcm_vars, surf_vars
+from .constants import LES_FIELDS
 from .coupler import default_coupler
 from .pipeline import CouplingPipeline
 

@@ -3,7 +3,6 @@ per-LES reference-shaped calls and the batched route must give the same numbers 
 import numpy as np
 import pytest
 
-import cases
 from conftest import relerr
 from oracle import numpy_batched as nb
 from sp_coupler_b200.constants import LES_FIELDS, TENDENCIES, gcm_vars, surf_vars
