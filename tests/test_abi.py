@@ -45,6 +45,38 @@ def test_sass_is_sm100a_with_tma_bulk():
     assert "LDS.128" in sass
 
 
+def test_production_kernels_do_not_spill():
+    """The streaming kernels run one CTA per SM with 12-16 warps: a register spill (stack frame) in any of the production
+    instantiations would put local-memory traffic on the HBM-bound path. cuobjdump reads it off the built library."""
+    import shutil
+    import subprocess
+    from sp_coupler_b200 import build
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", build.build()], capture_output=True, text=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        line = line.strip()
+        if line.startswith("Function "):
+            name = line[len("Function "):].rstrip(":")
+        elif line.startswith("REG:") and name:
+            usage[name] = {k: int(v) for k, v in (kv.split(":") for kv in line.split() if kv.split(":")[1].isdigit())}
+    production = {
+        "slab_reduce_tma_kernelIfNS_4RingILi16ELi8192ELi1ELb0ELi1ELi1E": 128,     # float32: 16 warps -> at most 128 registers
+        "slab_reduce_tma_kernelIdNS_4RingILi12ELi8192ELi1ELb0ELi1ELi1E": 168,     # float64: 12 warps
+        "slab_reduce_tma_pair_kernelIfLi12E": 168,
+        "slab_reduce_ijk_tma_kernelIfLi5ENS_7IjkRingILi12ELi8192ELi2E": 168,
+        "slab_reduce_ijk_tma_kernelIdLi5ENS_7IjkRingILi12ELi8192ELi2E": 168,
+    }
+    for frag, max_regs in production.items():
+        hits = [u for n, u in usage.items() if frag in n]
+        assert hits, "kernel %s not found in the library" % frag
+        for u in hits:
+            assert u["STACK"] == 0 and u["LOCAL"] == 0, (frag, u)
+            assert u["REG"] <= max_regs, (frag, u)
+
+
 def test_struct_layouts_match_header_compiled_as_c(tmp_path):
     """The header must be plain C (what a cgo / Fortran-C / ctypes-gen consumer compiles) and every field of the
     ctypes mirror must sit at the offset gcc gives it."""
