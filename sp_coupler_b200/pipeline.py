@@ -281,6 +281,8 @@ class CouplingPipeline(object):
         self.zf = torch.as_tensor(np.asarray(zf, dtype=np.float64)).to(dev)
         self.zh = torch.as_tensor(np.asarray(zh, dtype=np.float64)).to(dev)
         self.nk = int(self.zf.shape[0])
+        self._zf_top = float(np.asarray(zf, dtype=np.float64)[-1])
+        self._tend_live = None
         self.ncol, self.nlev, self.dtype = ncol, nlev, dtype
         self.couple_surface, self.layout, self.ql_thresh = couple_surface, layout, ql_thresh
         self.staging = GcmStaging(ncol, nlev, dtype, dev)
@@ -408,14 +410,39 @@ class CouplingPipeline(object):
         self.cpl.launches += self._graph_launches
         return self._graph_frc
 
-    def step_host(self, dt=900.0, f_les=1.0, f_gcm=1.0, owner=0):
+    def first_live_level(self):
+        """Host-side bound of where tendencies can be non-zero: the smallest start_index over this rank's columns
+        (spcpl.py:494-498: GCM full levels strictly above the LES top get zero), computed from the staged HOST
+        profiles with the kernels' own float64 expression (Zgfull - Zghalf[-1]) / grav > zf[-1], minus one level of
+        margin. Levels [0, first_live) of every tendency are exactly zero and need not travel."""
+        h = self.staging.host
+        zf = (h["Zgfull"].double() - h["Zghalf"].double()[:, -1:]) / 9.81
+        start = (zf > float(self._zf_top)).sum(dim=1)
+        return max(int(start.min()) - 1, 0)
+
+    def step_host(self, dt=900.0, f_les=1.0, f_gcm=1.0, owner=0, compact=False):
         """The step as the host GCM sees it: GCM profiles in pinned host memory in, tendencies in
-        pinned host memory out on the rank that owns the GCM. Synchronises before returning."""
+        pinned host memory out on the rank that owns the GCM. Synchronises before returning.
+        compact=True (single rank): only the levels that can be non-zero come back - returns
+        (forcings, (tend[:, :, first:], first)) with the block contiguous in pinned memory; `first` comes from
+        first_live_level(), evaluated on the host while the GPU runs the step."""
         self.staging.upload()
         if self._graph is not None and self._graph_args == (dt, f_les, f_gcm):
             frc = self.step_graph()
         else:
             frc = self.step_device(dt, f_les, f_gcm)
+        if compact and not self.gather:
+            first = self.first_live_level()
+            nl = self.nlev - first
+            if self._tend_live is None:
+                self._tend_live = torch.empty(self.tend.numel(), dtype=self.dtype, device=self.cpl.device)
+            n = self.ncol * 7 * nl
+            dev = self._tend_live[:n].view(self.ncol, 7, nl)
+            dev.copy_(self.tend[:, :, first:])                      # strided -> contiguous, on the device
+            host = self.tend_host.view(-1)[:n].view(self.ncol, 7, nl)
+            host.copy_(dev, non_blocking=True)
+            torch.cuda.current_stream(self.cpl.device).synchronize()
+            return frc, (host, first)
         if self.rank == owner:
             self.tend_host.copy_(self.tend_all, non_blocking=True)
         torch.cuda.current_stream(self.cpl.device).synchronize()

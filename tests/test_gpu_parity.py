@@ -409,3 +409,32 @@ def test_cuda_graph_step_is_bit_identical(cpl, cuda_device, ncol):
         for k in ("prof", "cnt", "mask"):
             assert torch.equal(eager.slab[k], graphed.slab[k]), k
     assert cpl.launches - l0 == 2 * 3 * 4      # both paths count K2, K1, projection, K3 per step
+
+
+@pytest.mark.parametrize("nlev", [19, 91, 137])
+def test_compact_host_tendencies(cpl, cuda_device, nlev):
+    """step_host(compact=True): only the levels that can be non-zero travel back. The block equals the full result
+    from its first level on, everything above is exactly zero in the full result, and the host-side bound is at
+    most one level looser than the kernel's start_index."""
+    import torch
+    from sp_coupler_b200 import synth
+    from sp_coupler_b200.pipeline import CouplingPipeline
+    ncol, nx, nk = 12, 16, 160
+    zf, zh = synth.les_grid(nk)
+    gcm = synth.make_gcm_columns(ncol, nlev, seed=21, dtype=np.float32)
+    aux = {k: torch.from_numpy(v).to(cuda_device) for k, v in synth.make_les_aux(ncol, nk, seed=21, dtype=np.float32).items()}
+    pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, torch.float32)
+    pipe.staging.fill_host(gcm)
+    pipe.staging.upload()
+    pipe.attach_les(synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=21), aux)
+    pipe.les_profiles()
+    _, full = pipe.step_host(900.0, 1.0, 1.0)
+    full = full.clone()
+    _, (live, first) = pipe.step_host(900.0, 1.0, 1.0, compact=True)
+    assert live.shape == (ncol, 7, nlev - first) and live.is_pinned() and live.is_contiguous()
+    assert torch.equal(live, full[:, :, first:])
+    assert not full[:, :, :first].any()
+    frc = pipe.forcings(900.0, 1.0)
+    tnd = cpl.les_to_gcm(pipe.gcm, pipe.zf, pipe.zh, pipe.slab, pipe.aux, frc["slab_idx"], 900.0, 1.0)
+    assert first == max(int(tnd["start_index"].min()) - 1, 0)
+    assert full[:, :, first + 1:].any()
