@@ -137,25 +137,37 @@ def test_slab_oracle_small():
 
 
 @pytest.mark.skipif(not ref_driver.available(), reason="/root/reference not present (GPU box)")
-def test_oracle_matches_reference_live():
+@pytest.mark.parametrize("nlev,nk,seed,dt,f_les,f_gcm,cons", [
+    (91, 160, 99, 900.0, 1.0, 1.0, False),
+    (19, 160, 7, 900.0, 1.0, 1.0, False),        # T21 test-case levels
+    (137, 160, 8, 600.0, 0.25, 2.0, False),      # non-unit factors, another time step
+    (91, 160, 9, 900.0, 1.0, 1.0, True),         # conservative coarsening
+    (137, 160, 10, 900.0, 0.5, 0.5, True),
+    (19, 20, 11, 900.0, 1.0, 1.0, False),        # spdummy-sized LES, dz = 200 m
+])
+def test_oracle_matches_reference_live(nlev, nk, seed, dt, f_les, f_gcm, cons):
+    """The restatement against the UNMODIFIED reference run here (oracle/ref_driver.py), beyond the committed golden
+    cases: other seeds (orography, surface pressure, fluxes), level sets, factors, and the conservative option."""
     from sp_coupler_b200 import synth
-    ncol, nlev, nk = 3, 91, 160
-    zf, zh = synth.les_grid(nk)
-    g = synth.make_gcm_columns(ncol, nlev, seed=99)
-    aux = synth.make_les_aux(ncol, nk, seed=99)
+    ncol = 3
+    zf, zh = synth.les_grid(nk, 25.0 if nk == 160 else 200.0)
+    g = synth.make_gcm_columns(ncol, nlev, seed=seed)
+    aux = synth.make_les_aux(ncol, nk, seed=seed)
     plan = synth.les_volume_plan(g, zf)
-    lp = {f: plan[f][0] for f in ("THL", "QT", "U", "V")}
-    lp["QL"] = np.full((ncol, nk), 3e-6)
-    A = np.linspace(0, 1, ncol * nlev).reshape(ncol, nlev)
-    r = ref_driver.run_columns(g, zf, zh, lp, aux, A, 900.0, 1.0, 1.0, True)
-    o = nb.set_les_forcings(g, zf, lp, aux["PS"], 900.0, 1.0, True)
+    rng = np.random.default_rng(seed)
+    lp = {f: plan[f][0] + plan[f][1] * 0.02 * rng.normal(size=plan[f][0].shape) for f in ("THL", "QT", "U", "V")}
+    lp["QL"] = np.maximum(4e-6 + 3e-6 * rng.normal(size=(ncol, nk)), 0.0)
+    A = rng.integers(0, 65, (ncol, nlev)) / 64.0
+    r = ref_driver.run_columns(g, zf, zh, lp, aux, A, dt, f_les, f_gcm, True, conservative=cons)
+    o = nb.set_les_forcings(g, zf, lp, aux["PS"], dt, f_les, True)
     for k in FORCING_KEYS:
         assert relerr(o[k], r[k]) <= 1e-13, k
-    lp2 = dict(lp, QL_ice=aux["QL_ice"], T=aux["T"])
-    t = nb.set_gcm_tendencies(g, zf, lp2, A, 900.0, 1.0)
+    lp2 = dict(lp, QL_ice=aux["QL_ice"], T=aux["T"], Rhobf=aux["Rhobf"])
+    t = nb.set_gcm_tendencies(g, zf, lp2, A, dt, f_gcm, conservative=cons, zh=zh)
     for k in TEND_KEYS:
         assert relerr(t[k], r[k]) <= 1e-13, k
     assert np.array_equal(t["start_index"], r["start_index"])
+    assert np.array_equal(nb.slab_indices(zh, r["gcm_Zh"]), r["slab_idx"])
 
 
 def test_oracle_integrals_match_reference_golden():
