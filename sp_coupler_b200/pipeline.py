@@ -139,6 +139,7 @@ class HostExchange(object):
                     tendency block device->host into `out[r*ncol:(r+1)*ncol]`, publishes "done"
         GCM owner   waits for all ranks: `out` holds [world*ncol][7][nlev], no device gather, no collective
 
+    Every rank owns the same number of columns (as with GcmScatter); the constructor checks that collectively,
     so the copies use every GPU's PCIe link at once instead of funnelling world*ncol columns through the
     owner GPU's link (reference analogue: the master gathers every profile over its own channels,
     spcpl.py:55-86, 535-542). Flags are int64 words in the same mapping (single writer each, monotonic).
@@ -163,6 +164,12 @@ class HostExchange(object):
         path = "/dev/shm/spcpl_b200_%s_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "r"), tag)
         # every phase ends in an all_reduce(MIN) of "it worked here", so that all ranks either get the buffer or raise
         # together - a rank that fails alone must never leave the others waiting in a collective
+        dev = "cuda" if torch.distributed.get_backend(group) == "nccl" else "cpu"
+        shape = torch.tensor([ncol, -ncol, nlev, -nlev], device=dev)
+        torch.distributed.all_reduce(shape, op=torch.distributed.ReduceOp.MIN, group=group)
+        if int(shape[0]) != -int(shape[1]) or int(shape[2]) != -int(shape[3]):
+            raise ValueError("HostExchange needs the same number of columns and levels on every rank "
+                             "(columns %d..%d, levels %d..%d)" % (int(shape[0]), -int(shape[1]), int(shape[2]), -int(shape[3])))
         err = None
         try:
             if rank == owner:

@@ -154,3 +154,29 @@ def test_host_exchange_shared_buffer(tmp_path):
         r = nb.coupling_step(g, zf, zh, vols, aux, aux["PS"], 900.0, 1.0, 1.0, True)
         want = np.stack([r["tendencies"][k] for k in TENDENCIES], axis=1)
         assert np.array_equal(np.load(str(tmp_path / ("out%d.npy" % it))), want), it
+
+
+def _unequal_worker(rank, world, port, outdir):
+    from sp_coupler_b200.pipeline import GcmStaging, HostExchange
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    st = GcmStaging(3 + rank, NLEV, torch.float64, "cpu", pin=False)      # 3 columns on rank 0, 4 on rank 1
+    try:
+        HostExchange(st, world, rank, owner=0, register=False, tag="uneq")
+        msg = "no error"
+    except ValueError as e:
+        msg = str(e)
+    open(os.path.join(outdir, "msg%d.txt" % rank), "w").write(msg)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_host_exchange_rejects_unequal_shards_on_every_rank(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_unequal_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        assert "same number of columns" in open(str(tmp_path / ("msg%d.txt" % rank))).read()
