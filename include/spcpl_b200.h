@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SPC_ABI_VERSION 1
+#define SPC_ABI_VERSION 2
 
 enum { SPC_F32 = 0, SPC_F64 = 1 };
 
@@ -61,6 +61,15 @@ const char* spc_last_error(void);
  * dynamic shared memory. No hidden per-step state. */
 int spc_create(spc_handle* out, int device);
 int spc_destroy(spc_handle h);
+
+/* Exchange buffers in HOST memory that K3 may store into directly (spc_gcm_tend.tend_peers / signal): the
+ * reference hands every tendency profile back to the host GCM (gcm.set_profile_tendency, spcpl.py:535-542).
+ * spc_host_register pins [p, p+nbytes) - e.g. a /dev/shm mapping shared by the ranks of a node - and maps it for the
+ * handle's device; spc_host_device_pointer returns the device-visible address of memory that is already pinned
+ * (cudaHostAlloc, torch pin_memory). */
+int spc_host_register(spc_handle h, void* p, size_t nbytes, void** dev_ptr);
+int spc_host_unregister(spc_handle h, void* p);
+int spc_host_device_pointer(spc_handle h, void* p, void** dev_ptr);
 
 /* ---------------------------------------------------------------------------------------------
  * K1  slab_reduce — replaces the LES-side slab averages the reference requests in
@@ -138,21 +147,42 @@ typedef struct {
   void* tend;           /* packed [ncol][7][nlev]: f_T,f_SH,f_QL,f_QI,f_U,f_V,f_A              */
   void* t;              /* optional [ncol][nk]  diagnostic temperature (spcpl.py:408-409)       */
   void* A_d;            /* optional [ncol][nlev] LES cloud fraction in GCM order (spcpl.py:404) */
-  int32_t* cntslab;     /* [ncol][nlev] projected cloudy-column count, ascending slabs; REQUIRED when the cloud
-                           fraction comes from les->mask (written by the projection kernel, read by K3) */
+  int32_t* cntslab;     /* optional [ncol][nlev] projected cloudy-column count, ascending slabs (the cloud fraction K3
+                           uses when it comes from les->mask). REQUIRED only for the IJK mask layout, where a separate
+                           projection kernel hands it to K3; the KJI projection runs inside K3 itself. */
   int32_t* bracket;     /* optional [ncol][nlev] upper_bound(zf, Zf)-1                          */
   int32_t* bracket_pf;  /* optional [ncol][nk]   upper_bound(Zf[::-1], zf)-1                    */
   int32_t* start_index; /* optional [ncol]       searchsorted(-Zf, -zf[-1]) (spcpl.py:498)      */
-  /* Fused gather (multi-GPU): besides `tend`, the kernel stores this rank's block straight into
-   * n_peers gather buffers [ncol_total][7][nlev] at column offset peer_col0 — peer-mapped device
-   * pointers (NVLink symmetric memory), so the tendencies reach the GCM-owning rank from K3's own
-   * epilogue instead of through a separate collective. tend_peers is a HOST array of n_peers
-   * (<= SPC_MAX_PEERS) device pointers; NULL / 0 disables it. */
+  /* Fused gather / host exchange: besides `tend`, the kernel stores this rank's block straight into
+   * n_peers remote buffers [ncol_total][7][nlev] at column offset peer_col0. A target is any address the
+   * device can write: a peer GPU's buffer mapped over NVLink (symmetric memory), or PINNED HOST memory of the
+   * process that owns the GCM (zero-copy stores over PCIe) - so the tendencies reach their consumer from K3's
+   * own epilogue instead of through a separate collective or copy (reference analogue: the 7
+   * gcm.set_profile_tendency calls per column, spcpl.py:535-542). tend_peers is a HOST array of
+   * n_peers*n_bufs device-visible pointers (target p of buffer set b at [b*n_peers + p]); NULL / 0 disables it. */
   void* const* tend_peers;
-  int n_peers;
+  int n_peers;          /* <= SPC_MAX_PEERS */
   int peer_col0;
+  /* Completion protocol of the launch (optional; sync == NULL disables it and n_bufs is taken as 1).
+   *   sync      DEVICE memory of this rank, SPC_SYNC_WORDS uint32 words, zeroed once by the caller:
+   *             [SPC_SYNC_EPOCH] launches completed so far, [SPC_SYNC_DONE] CTA counter (kernel-internal),
+   *             [SPC_SYNC_ERROR] non-zero after a wait timed out (20 s), [SPC_SYNC_FLAG0 + s] flag of slot s.
+   *   The launch with epoch e stores into buffer set (e % n_bufs). When its last CTA has finished and every store
+   *   of the launch is visible system-wide, word SPC_SYNC_FLAG0 + sync_slot of each of the n_signal blocks in
+   *   `signal` (HOST array of device-visible pointers: peer sync blocks, or a block in pinned host memory that the
+   *   host polls) is set to e+1 with release semantics; then the kernel waits until the flags of slots
+   *   [0, n_wait) of its OWN block have reached e+1 (a barrier over n_wait ranks when every rank signals every
+   *   rank), and sets its epoch to e+1. Everything is inside the kernel: the step stays capturable in a CUDA graph. */
+  int n_bufs;           /* 1 or 2 */
+  uint32_t* sync;
+  uint32_t* const* signal;
+  int n_signal;         /* <= SPC_MAX_PEERS + 1 */
+  int sync_slot;
+  int n_wait;           /* <= SPC_SYNC_MAX_SLOTS */
 } spc_gcm_tend;
 #define SPC_MAX_PEERS 16
+enum { SPC_SYNC_EPOCH = 0, SPC_SYNC_DONE = 1, SPC_SYNC_ERROR = 2, SPC_SYNC_FLAG0 = 8, SPC_SYNC_MAX_SLOTS = 32,
+       SPC_SYNC_WORDS = 64 };
 
 int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, const double* zh, int nk,
                    const spc_les_prof* les, double dt, double factor, int conservative,
@@ -205,7 +235,9 @@ int spc_set_les_state(spc_handle h, const double* prof, double amp, uint32_t str
  * scale the qt fluctuations by it; additive zero-mean noise a*R when beta hits 5; optional constant-T
  * theta_l correction. KJI layout. qt (and thl) are updated in place.
  *   status bits: 1 multiplicative root, 2 nudged to barely unsaturated, 4 additive root,
- *                8 multiplicative bracket failed, 16 additive root not bracketed / R missing. */
+ *                8 multiplicative bracket failed, 16 additive root not bracketed / R missing,
+ *                32 a root search stopped at its iteration limit (scipy raises in cases 16 and 32; the host
+ *                mirror sp_coupler_b200/nudge.py raises on them too). */
 typedef struct {
   void* qt;              /* in/out [ncol][nk][ny][nx]                                            */
   const void* qsat;      /* [ncol][nk][ny][nx] saturation humidity (les.get_field("Qsat")), or NULL */

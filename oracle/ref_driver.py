@@ -1,9 +1,11 @@
-"""Runs the UNMODIFIED reference coupler (/root/reference/splib/{spcpl,sputils}.py) per column
-under the unit shim in oracle/stubs — TEST INFRASTRUCTURE ONLY.
+"""Runs the UNMODIFIED reference coupler (splib/{spcpl,sputils}.py) per column under the unit shim in
+oracle/stubs — TEST / BASELINE INFRASTRUCTURE ONLY.
 
-Works only where /root/reference exists (the build container); it is used to
-(1) validate oracle/numpy_batched.py and (2) generate the golden vectors committed under
-tests/golden/ (oracle/make_golden.py). Nothing on the GPU box imports this module.
+The reference modules are imported from /root/reference where that tree exists (the build container), else from
+the verbatim copy oracle/make_ref.py placed in the git-ignored oracle/_ref/ (which travels to the GPU box). Used to
+(1) validate oracle/numpy_batched.py, (2) generate the golden vectors committed under tests/golden/
+(oracle/make_golden.py), and (3) time the reference's own per-column coupling functions on the host cores
+(bench.py --impl reference and its cpu_baseline leg: reference_column_steps below). The product never imports it.
 """
 import contextlib
 import io
@@ -11,8 +13,18 @@ import os
 import sys
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("SPC_REFERENCE_ROOT", "/root/reference")
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STUBS = os.path.join(_HERE, "stubs")
+
+
+def _reference_root():
+    for root in (os.environ.get("SPC_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if root and os.path.isfile(os.path.join(root, "splib", "spcpl.py")):
+            return root
+    return os.environ.get("SPC_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def available():
@@ -169,4 +181,54 @@ def run_variability_nudge(fields, profiles, presf, ql_ref, DT, constantT, seed):
                qt_std=np.array(captured["qt_std"], dtype=np.float64))
     if constantT:
         out["thl"] = np.array(les.fields.THL, dtype=np.float64)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ timing
+def reference_column_steps(gcm, zf, zh, vols, aux, dt, f_les, f_gcm, couple_surface=True, ql_thresh=0.0):
+    """BASELINE.md §2 "B-ref": the coupling step of every column of the block, serially, as splib.step runs it
+    (splib.py:317-332) - numpy slab means of the five volumes + above-threshold ql count and projected cloud cover
+    (the LES worker's part, spcpl.py:748-765), then the UNMODIFIED spcpl.set_les_forcings and
+    spcpl.set_gcm_tendencies with write=False. vols: dict field -> [ncol][nk][ny][nx] in the storage dtype.
+    Returns the packed tendencies [ncol][7][nlev] (so the work cannot be optimised away and can be checked)."""
+    sputils, spcpl, spdummy, spio = load_reference()
+    from _q import Q
+    spio.write_les_data = lambda les, **kw: None          # convert_profiles is called with its default write=True
+    ncol, nlev = gcm["T"].shape
+    nk = len(zf)
+    zfq, zhq = Q(np.asarray(zf, dtype=np.float64)), Q(np.asarray(zh, dtype=np.float64))
+    out = np.empty((ncol, 7, nlev))
+    names = ("T", "SH", "QL", "QI", "U", "V", "A")
+    devnull = io.StringIO()
+    for c in range(ncol):
+        les = _Les(c)
+        for v in spcpl.gcm_vars:                          # gather_gcm_data's per-LES attributes (spcpl.py:81-86)
+            setattr(les, v, Q(np.asarray(gcm[v][c], dtype=np.float64)))
+        for v in spcpl.surf_vars:
+            setattr(les, v, Q(np.float64(gcm[v][c])))
+        les.zf_cache, les.zh_cache = zfq, zhq
+        les.rain = Q(0.0)
+        prof = {}
+        for f in ("U", "V", "THL", "QT", "QL"):           # les.get_profile_*: horizontal slab means
+            prof[f] = Q(vols[f][c].reshape(nk, -1).mean(axis=1).astype(np.float64))
+        cloudy = vols["QL"][c].reshape(nk, -1) > ql_thresh
+        for k in ("presf", "Rhof", "Rhobf", "QL_ice", "QR", "T"):
+            prof[k] = Q(np.asarray(aux[k][c], dtype=np.float64))
+        prof["PS"] = Q(np.float64(aux["PS"][c]))
+        prof["Rain"] = Q(np.float64(aux["Rain"][c]))
+        g = _Gcm()
+        spcpl.set_les_forcings(les, None, False, False, prof, dt, f_les, couple_surface, write=False)
+        idx = np.asarray(sputils.searchsorted(les.zh_cache, les.gcm_Zh, side="right")[:-1:][::-1])   # spcpl.py:761-764
+        A = np.zeros(nlev)                                # les.get_cloudfraction(indices): projected cover per slab
+        k0 = 0
+        for r in range(nlev):
+            k1 = min(max(int(idx[r]), k0), nk)
+            if k1 > k0:
+                A[r] = np.count_nonzero(cloudy[k0:k1].any(axis=0)) / cloudy.shape[1]
+            k0 = k1
+        prof["A"] = Q(A)
+        with contextlib.redirect_stdout(devnull):
+            spcpl.set_gcm_tendencies(g, les, prof, dt, f_gcm, write=False)
+        for n, name in enumerate(names):
+            out[c, n] = g.tend[c][name]
     return out

@@ -6,16 +6,21 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libspcpl_b200.so")
+# SPCPL_B200_LIB: alternative build of the same ABI (tools/*_probe.py point it at libspcpl_b200_tune.so, the -DSPC_TUNING
+# build that adds the sweep variants and per-handle tuning setters); the package itself always loads the production library
+LIB_PATH = os.environ.get("SPCPL_B200_LIB") or os.path.join(HERE, "lib", "libspcpl_b200.so")
 
 SPC_F32, SPC_F64 = 0, 1
 LAYOUT_KJI, LAYOUT_IJK = 0, 1
 NFIELDS, NTEND = 5, 7
+ABI_VERSION = 2
+SYNC_EPOCH, SYNC_DONE, SYNC_ERROR, SYNC_FLAG0, SYNC_MAX_SLOTS, SYNC_WORDS = 0, 1, 2, 8, 32, 64
+MAX_PEERS = 16
 
 # every symbol include/spcpl_b200.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = ["spc_abi_version", "spc_last_error", "spc_create", "spc_destroy", "spc_mask_words_per_column",
            "spc_slab_reduce", "spc_gcm_to_les", "spc_les_to_gcm", "spc_cloud_fraction", "spc_interp", "spc_searchsorted", "spc_exner", "spc_interp_c",
-           "spc_set_les_state", "spc_variability_nudge"]
+           "spc_set_les_state", "spc_variability_nudge", "spc_host_register", "spc_host_unregister", "spc_host_device_pointer"]
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
 
@@ -43,7 +48,8 @@ class LesProf(C.Structure):
 class GcmTend(C.Structure):
     """struct spc_gcm_tend"""
     _fields_ = [(n, _vp) for n in ("tend", "t", "A_d", "cntslab", "bracket", "bracket_pf", "start_index", "tend_peers")] + \
-               [("n_peers", _i), ("peer_col0", _i)]
+               [("n_peers", _i), ("peer_col0", _i), ("n_bufs", _i), ("sync", _vp), ("signal", _vp), ("n_signal", _i),
+                ("sync_slot", _i), ("n_wait", _i)]
 
 
 class NudgeIO(C.Structure):
@@ -82,6 +88,12 @@ def lib():
     L.spc_interp_c.argtypes = [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]
     L.spc_set_les_state.argtypes = [_vp, _vp, _d, C.c_uint32, C.c_uint32, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]
     L.spc_variability_nudge.argtypes = [_vp, C.POINTER(NudgeIO), _i, _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp]
+    L.spc_host_register.argtypes = [_vp, _vp, C.c_size_t, C.POINTER(_vp)]
+    L.spc_host_unregister.argtypes = [_vp, _vp]
+    L.spc_host_device_pointer.argtypes = [_vp, _vp, C.POINTER(_vp)]
+    if L.spc_abi_version() != ABI_VERSION:
+        raise RuntimeError("sp_coupler_b200: %s has ABI version %d, this package needs %d: rebuild it with "
+                           "`python -m sp_coupler_b200.build --force`" % (LIB_PATH, L.spc_abi_version(), ABI_VERSION))
     for name in SYMBOLS:
         f = getattr(L, name)
         if f.restype is C.c_int and name not in ("spc_abi_version",):

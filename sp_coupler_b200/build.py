@@ -19,7 +19,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libspcpl_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "--compress-mode=size", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 # translation unit -> extra flags. The profile kernels are compiled without FMA contraction so
 # that float64 results are bit-identical to numpy's ("Numerics").
 SOURCES = {
@@ -45,27 +45,36 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+TUNE_LIB = os.path.join(LIBDIR, "libspcpl_b200_tune.so")
+
+
+def build(force=False, verbose=False, tune=False):
+    """Production library (tune=False): only the kernel shapes the dispatch uses, no mutable global state.
+    tune=True builds libspcpl_b200_tune.so with -DSPC_TUNING: the ring-shape sweep variants and the per-handle
+    tuning setters (spc_tune_k1, spc_tune_profiles) that tools/*_probe.py drive; never loaded by the package."""
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
+    objdir = os.path.join(OBJDIR, "tune") if tune else OBJDIR
+    os.makedirs(objdir, exist_ok=True)
+    lib = TUNE_LIB if tune else LIB
     headers = [os.path.join(ROOT, "include", "spcpl_b200.h"), os.path.join(CSRC, "spc_common.cuh"), __file__]
     objs, rebuilt = [], False
     for src, extra in SOURCES.items():
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc()] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc()] + ARCH + COMMON + extra + (["-DSPC_TUNING"] if tune else []) + \
+                  (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
             rebuilt = True
-    if rebuilt or not os.path.exists(LIB):
-        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs
+    if rebuilt or not os.path.exists(lib):
+        cmd = [nvcc()] + ARCH + ["-shared", "-o", lib] + objs
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 TORCH_LIB = os.path.join(LIBDIR, "spcpl_b200_torch.so")
@@ -97,5 +106,7 @@ def build_torch_ext(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--tune" in sys.argv:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, tune=True))
     if "--torch" in sys.argv:
         print(build_torch_ext(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

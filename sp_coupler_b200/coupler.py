@@ -22,6 +22,46 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+class RemoteTargets(object):
+    """Where K3 sends this rank's tendency block besides its local buffer, and how the launch reports completion
+    (struct spc_gcm_tend: tend_peers / sync / signal, include/spcpl_b200.h). Built once, reused every step; holds the
+    ctypes arrays alive.
+
+      targets    list of buffer sets, each a list of device-visible addresses of [ncol_total][7][nlev] buffers
+                 (peer GPU memory over NVLink, or pinned host memory); 1 or 2 sets, used alternately
+      col0       column offset of this rank's block inside a target
+      sync       this rank's sync block (int32 device tensor of _abi.SYNC_WORDS words, zeroed) or None
+      signal     addresses of the sync blocks whose flag [slot] the launch sets when all its stores are visible
+      n_wait     the launch then waits for flags [0, n_wait) of its own block (device-side barrier)"""
+
+    def __init__(self, targets=(), col0=0, sync=None, signal=(), slot=0, n_wait=0):
+        sets = [list(t) for t in targets if len(t)]
+        if len(sets) not in (0, 1, 2) or any(len(t) != len(sets[0]) for t in sets):
+            raise ValueError("targets: one or two buffer sets of equal length")
+        self.n_bufs = max(len(sets), 1)
+        self.n_peers = len(sets[0]) if sets else 0
+        if self.n_peers > _abi.MAX_PEERS or len(signal) > _abi.MAX_PEERS + 1:
+            raise ValueError("at most %d targets" % _abi.MAX_PEERS)
+        if len(sets) == 2 and sync is None:
+            raise ValueError("two buffer sets alternate by the sync epoch: pass a sync block")
+        flat = [int(p) for t in sets for p in t]
+        self._parr = (C.c_void_p * max(len(flat), 1))(*flat)
+        self._sarr = (C.c_void_p * max(len(signal), 1))(*[int(p) for p in signal])
+        self.col0, self.sync, self.n_signal, self.slot, self.n_wait = int(col0), sync, len(signal), int(slot), int(n_wait)
+        if sync is not None and (sync.dtype != torch.int32 or sync.numel() < _abi.SYNC_WORDS or not sync.is_contiguous()):
+            raise ValueError("sync must be a contiguous int32 tensor of %d words" % _abi.SYNC_WORDS)
+
+    def fill(self, o):
+        if self.n_peers:
+            o.tend_peers = C.cast(self._parr, C.c_void_p)
+            o.n_peers, o.peer_col0 = self.n_peers, self.col0
+        o.n_bufs = self.n_bufs
+        if self.sync is not None:
+            o.sync = self.sync.data_ptr()
+            o.signal = C.cast(self._sarr, C.c_void_p)
+            o.n_signal, o.sync_slot, o.n_wait = self.n_signal, self.slot, self.n_wait
+
+
 class Coupler(object):
     """Per-device entry point. All methods are asynchronous on torch's current stream."""
 
@@ -47,6 +87,25 @@ class Coupler(object):
             self.close()
         except Exception:
             pass
+
+    # ------------------------------------------------------------------ host exchange memory
+    def host_register(self, tensor):
+        """Pin the host memory of a CPU tensor (e.g. a /dev/shm mapping shared by the ranks of a node) and map it for
+        this device; returns the device-visible address K3 may store into (RemoteTargets)."""
+        dp = C.c_void_p()
+        _abi.check(self._lib.spc_host_register(self._h, C.c_void_p(tensor.data_ptr()), tensor.numel() * tensor.element_size(),
+                                               C.byref(dp)), "spc_host_register")
+        return int(dp.value)
+
+    def host_unregister(self, tensor):
+        _abi.check(self._lib.spc_host_unregister(self._h, C.c_void_p(tensor.data_ptr())), "spc_host_unregister")
+
+    def host_device_pointer(self, tensor):
+        """Device-visible address of an already pinned CPU tensor (torch pin_memory)."""
+        dp = C.c_void_p()
+        _abi.check(self._lib.spc_host_device_pointer(self._h, C.c_void_p(tensor.data_ptr()), C.byref(dp)),
+                   "spc_host_device_pointer")
+        return int(dp.value)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -105,21 +164,25 @@ class Coupler(object):
             ncol, nx, ny, nk = v[0].shape
         for i, t in enumerate(v):
             self._chk(t, "vol[%s]" % LES_FIELDS[i], dtype, v[0].shape)
+        # buffers of a previous result are reused only if they still fit this call (shape, dtype, device): a stale
+        # mask or count buffer of another shape / layout would be written out of bounds
         out = {} if out is None else out
-        prof = out.get("prof")
-        if prof is None:
-            prof = self._empty((5, ncol, nk), torch.float64)
-        cnt = out.get("cnt") if want_cnt else None
-        if want_cnt and cnt is None:
-            cnt = self._empty((ncol, nk), torch.int32)
+
+        def reuse(name, shape, dt_):
+            t = out.get(name)
+            if isinstance(t, torch.Tensor) and tuple(t.shape) == tuple(shape) and t.dtype == dt_ and \
+                    t.device == self.device and t.is_contiguous():
+                return t
+            return self._empty(shape, dt_)
+
+        prof = reuse("prof", (5, ncol, nk), torch.float64)
+        cnt = reuse("cnt", (ncol, nk), torch.int32) if want_cnt else None
         mask = None
         if want_mask:
             mw = self.mask_words_per_column(dtype, lay, nx, ny, nk)
             if mw == 0:
                 raise RuntimeError("no cloud-mask format for layout %r; pass want_mask=False" % (layout,))
-            mask = out.get("mask")
-            if mask is None:
-                mask = self._empty((ncol, mw), torch.int32)
+            mask = reuse("mask", (ncol, mw), torch.int32)
         arr = (C.c_void_p * 5)(*[t.data_ptr() for t in v])
         _abi.check(self._lib.spc_slab_reduce(self._h, arr, _DT[dtype], lay, ncol, nx, ny, nk, float(ql_thresh),
                                              _ptr(prof), _ptr(cnt), _ptr(mask), self._stream()), "spc_slab_reduce")
@@ -127,10 +190,24 @@ class Coupler(object):
         return dict(prof=prof, cnt=cnt, mask=mask, nx=nx, ny=ny, dtype=dtype, layout=lay)
 
     # ------------------------------------------------------------------ K2
+    def _alloc_into(self, res, o, out):
+        """alloc(name, shape, dtype): take a fitting tensor from `out` (validated) or allocate; record it in the
+        result dict and in the ctypes struct."""
+        def alloc(name, shape, dt_):
+            t = out.get(name) if out else None
+            if t is None:
+                t = self._empty(shape, dt_)
+            else:
+                self._chk(t, "out[%r]" % name, dt_, shape)
+            res[name] = t
+            setattr(o, name, t.data_ptr())
+        return alloc
+
     def gcm_to_les(self, gcm, zf, zh=None, les_prof=None, ps_les=None, dt=900.0, factor=1.0,
-                   couple_surface=True, diagnostics=False, want_state=False, want_bracket=False):
+                   couple_surface=True, diagnostics=False, want_state=False, want_bracket=False, out=None):
         """convert_profiles + set_les_forcings arithmetic + convert_surface_fluxes for all columns
-        (spcpl.py:171-246, 299-385, 136-167). Returns a dict of output tensors."""
+        (spcpl.py:171-246, 299-385, 136-167). Returns a dict of output tensors; `out` (a previous result of the same
+        call shape) is written in place instead of allocating."""
         s, ncol, nlev, dtype = self._gcm_struct(gcm, couple_surface)
         nk = zf.shape[0]
         self._chk(zf, "zf", torch.float64, (nk,))
@@ -142,29 +219,24 @@ class Coupler(object):
             self._chk(ps_les, "ps_les", dtype, (ncol,))
         o = _abi.LesForcing()
         res = {}
-
-        def alloc(name, shape, dt_=dtype):
-            t = self._empty(shape, dt_)
-            res[name] = t
-            setattr(o, name, t.data_ptr())
-
-        alloc("ql_ref", (ncol, nk))
-        alloc("ps", (ncol,))
+        alloc = self._alloc_into(res, o, out)
+        alloc("ql_ref", (ncol, nk), dtype)
+        alloc("ps", (ncol,), dtype)
         if les_prof is not None:
             for n in ("f_u", "f_v", "f_thl", "f_qt", "f_ql"):
-                alloc(n, (ncol, nk))
+                alloc(n, (ncol, nk), dtype)
         if ps_les is not None:
-            alloc("f_ps", (ncol,))
+            alloc("f_ps", (ncol,), dtype)
         if want_state:
             for n in ("u", "v", "thl", "qt"):
-                alloc(n, (ncol, nk))
+                alloc(n, (ncol, nk), dtype)
         if couple_surface:
             for n in ("z0m", "z0h", "wthl", "wqt"):
-                alloc(n, (ncol,))
+                alloc(n, (ncol,), dtype)
         if diagnostics:
             for n in ("Tv", "THL", "QT", "Zf"):
-                alloc(n, (ncol, nlev))
-            alloc("Zh", (ncol, nlev + 1))
+                alloc(n, (ncol, nlev), dtype)
+            alloc("Zh", (ncol, nlev + 1), dtype)
         if want_bracket:
             alloc("bracket", (ncol, nk), torch.int32)
         if zh is not None:
@@ -177,10 +249,12 @@ class Coupler(object):
 
     # ------------------------------------------------------------------ K3
     def les_to_gcm(self, gcm, zf, zh, slab, aux, slab_idx=None, dt=900.0, factor=1.0, conservative=False,
-                   A=None, diagnostics=False, tend_out=None, peer_ptrs=None, peer_col0=0):
+                   A=None, diagnostics=False, tend_out=None, peer_ptrs=None, peer_col0=0, remote=None, out=None):
         """set_gcm_tendencies for all columns (spcpl.py:388-555) incl. the projected cloud fraction.
 
         slab: result of slab_reduce (or a dict with 'prof'); aux: dict QL_ice, T (+Rhobf) [ncol,nk].
+        remote: RemoteTargets - K3 also stores the block into peer GPUs / pinned host memory and runs the completion
+        protocol (peer_ptrs / peer_col0: shorthand for one buffer set without sync).
         Returns dict(tend=[ncol,7,nlev], named views f_T.., A_d, start_index, ...)."""
         s, ncol, nlev, dtype = self._gcm_struct(gcm, False)
         nk = zf.shape[0]
@@ -193,43 +267,44 @@ class Coupler(object):
         lp.T = self._chk(aux["T"], "T", dtype, (ncol, nk)).data_ptr()
         if conservative:
             lp.Rhobf = self._chk(aux["Rhobf"], "Rhobf", dtype, (ncol, nk)).data_ptr()
+        ijk_mask = False
         if A is not None:
             lp.A = self._chk(A, "A", dtype, (ncol, nlev)).data_ptr()
         elif slab.get("mask") is not None:
             if slab_idx is None:
                 raise ValueError("slab_idx (from gcm_to_les) is needed to project the cloud mask")
-            lp.mask = slab["mask"].data_ptr()
+            mw = self.mask_words_per_column(slab["dtype"], slab["layout"], slab["nx"], slab["ny"], nk)
+            lp.mask = self._chk(slab["mask"], "slab.mask", torch.int32, (ncol, mw)).data_ptr()
             lp.slab_idx = self._chk(slab_idx, "slab_idx", torch.int32, (ncol, nlev)).data_ptr()
             if slab.get("cnt") is not None:
-                lp.cnt = slab["cnt"].data_ptr()
+                lp.cnt = self._chk(slab["cnt"], "slab.cnt", torch.int32, (ncol, nk)).data_ptr()
             lp.vol_dtype, lp.layout, lp.nx, lp.ny = _DT[slab["dtype"]], slab["layout"], slab["nx"], slab["ny"]
+            ijk_mask = slab["layout"] == _abi.LAYOUT_IJK
         o = _abi.GcmTend()
+        if tend_out is None and out and out.get("tend") is not None:
+            tend_out = out["tend"]
         tend = tend_out if tend_out is not None else self._empty((ncol, 7, nlev), dtype)
         self._chk(tend, "tend", dtype, (ncol, 7, nlev))
         o.tend = tend.data_ptr()
-        if peer_ptrs:       # fused gather: K3 also stores into peer-mapped gather buffers (NVLink)
-            parr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
-            o.tend_peers = C.cast(parr, C.c_void_p)
-            o.n_peers, o.peer_col0 = len(peer_ptrs), int(peer_col0)
+        o.n_bufs = 1
+        if remote is None and peer_ptrs:
+            remote = RemoteTargets([list(peer_ptrs)], peer_col0)
+        if remote is not None:      # K3 also stores into remote buffers (NVLink peers / pinned host) and signals completion
+            remote.fill(o)
         res = {"tend": tend}
-
-        def alloc(name, shape, dt_=dtype):
-            t = self._empty(shape, dt_)
-            res[name] = t
-            setattr(o, name, t.data_ptr())
-
-        alloc("A_d", (ncol, nlev))
+        alloc = self._alloc_into(res, o, out)
+        alloc("A_d", (ncol, nlev), dtype)
         alloc("start_index", (ncol,), torch.int32)
         if lp.mask:
             alloc("cntslab", (ncol, nlev), torch.int32)
         if diagnostics:
-            alloc("t", (ncol, nk))
+            alloc("t", (ncol, nk), dtype)
             alloc("bracket", (ncol, nlev), torch.int32)
             alloc("bracket_pf", (ncol, nk), torch.int32)
         _abi.check(self._lib.spc_les_to_gcm(self._h, C.byref(s), _ptr(zf), _ptr(zh), nk, C.byref(lp), float(dt),
                                             float(factor), int(bool(conservative)), C.byref(o), self._stream()),
                    "spc_les_to_gcm")
-        self.launches += 2 if lp.mask else 1      # cloud projection kernel + tendency kernel
+        self.launches += 2 if ijk_mask else 1     # IJK mask: its projection kernel + K3; KJI: the projection is K3's prologue
         for i, n in enumerate(TENDENCIES):
             res[n] = tend[:, i, :]
         return res

@@ -19,7 +19,7 @@ constexpr double kRtol = 4 * DBL_EPSILON;          // _rtol = 4 * eps
 constexpr int kMaxIter = 100;                      // _iter
 constexpr double kBetaMax = 5.0;                   // spcpl.py:654-655, 702-703
 
-enum { ST_MULT = 1, ST_UNSAT = 2, ST_ADD = 4, ST_NOBRACKET = 8, ST_ADD_FAIL = 16 };
+enum { ST_MULT = 1, ST_UNSAT = 2, ST_ADD = 4, ST_NOBRACKET = 8, ST_ADD_FAIL = 16, ST_NOCONV = 32 };
 
 struct NudgeArgs {
   void* qt;
@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(kThreads) nudge_kernel(const NudgeArgs a) {
       int bs;
       beta = brentq([&](double b) { return ql_diff(s, b, qt_av, ql_ref, red); }, 0.0, kBetaMax, bs);   // :672
       st |= ST_MULT;
+      if (bs == -2) st |= ST_NOCONV;                               // scipy would raise RuntimeError (maxiter) here
     }
   } else if (ql_av > ql_ref) {                                     // spcpl.py:675-691
     // argmax(qt - qsat) over the slab, first maximum in the reference's (i, j) C order
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(kThreads) nudge_kernel(const NudgeArgs a) {
         else {
           additive = true;
           st |= ST_ADD;
+          if (bs == -2) st |= ST_NOCONV;
         }
       } else {
         st |= ST_ADD_FAIL;

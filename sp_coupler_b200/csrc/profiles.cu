@@ -13,8 +13,7 @@ namespace {
 using namespace spc;
 
 constexpr int kThreads = 256;
-int g_k2_threads = 0, g_k3_threads = 0;  // tuning hook (spc_tune_profiles); 0 = from the shape
-int g_proj_threads = 0;                  // threads of the cloud projection CTA; 0 = by mask row size (64 up to 512 B per level, else 256)
+// (spc_ctx.k2_threads / k3_threads / proj_threads: tuning overrides, always 0 in the production library)
 
 // Threads per column CTA: one per level of the longer of the two profiles, whole warps, at most kThreads.
 // (256 threads for 137 / 160 levels left three of eight warps idle and capped the resident useful warps.)
@@ -159,9 +158,15 @@ struct K3Args {
   spc_gcm_tend o;
   double dt, factor;
   int nk, conservative;
-  void* peers[SPC_MAX_PEERS];  // fused gather targets (peer-mapped gather buffers), see spc_gcm_tend
-  int n_peers;
-  size_t peer_off;      // element offset of this rank's block inside a gather buffer
+  int project_mw;       // > 0: the KJI cloud projection runs in this kernel's prologue; mask words per level
+  // fused gather / host exchange targets (spc_gcm_tend): n_peers targets x n_bufs buffer sets
+  void* peers[2 * SPC_MAX_PEERS];
+  int n_peers, n_bufs;
+  size_t peer_off;      // element offset of this rank's block inside a target buffer
+  // completion protocol (spc_gcm_tend.sync)
+  uint32_t* sync;
+  uint32_t* signal[SPC_MAX_PEERS + 1];
+  int n_signal, sync_slot, n_wait;
 };
 
 // sputils.integral, weighted branch (sputils.py:94-161), a <= b guaranteed by the caller
@@ -184,6 +189,32 @@ __device__ double integral_w(double a, double b, const double* z, int n, const d
   return (S - Sa - Sb) / (Sw - Swa - Swb);                              // sputils.py:161
 }
 
+// The same integral for NF profiles that share the edges z and the weights w (the seven interp_c calls of
+// spcpl.py:480-486 differ only in q): the two cell searches, the weight sums and the edge lengths are
+// evaluated once, and every field sees exactly the operations, in the order, of integral_w - the results are
+// bit-identical to NF separate calls. q[f] are [n-1] cell values; z, w, q live in shared memory.
+template <int NF>
+__device__ __forceinline__ void integral_w_multi(double a, double b, const double* z, int n, const double* const (&q)[NF],
+                                                 const double* w, double (&out)[NF]) {
+  int ia = 0;
+  while (ia + 1 < n - 1 && z[ia + 1] < a) ++ia;
+  int ib = ia;
+  while (ib + 1 < n - 1 && z[ib + 1] < b) ++ib;
+  double S[NF], Sw = 0.0;
+#pragma unroll
+  for (int f = 0; f < NF; ++f) S[f] = 0.0;
+  for (int i = ia; i <= ib; ++i) {
+    const double dz = z[i + 1] - z[i], wi = w[i];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) S[f] += wi * q[f][i] * dz;
+    Sw += wi * dz;
+  }
+  const double da = a - z[ia], db = z[ib + 1] - b, wa = w[ia], wb = w[ib];
+  const double den = Sw - wa * da - wb * db;
+#pragma unroll
+  for (int f = 0; f < NF; ++f) out[f] = (S[f] - wa * q[f][ia] * da - wb * q[f][ib] * db) / den;
+}
+
 // ---- projected cloud cover per GCM slab (les.get_cloudfraction(indices), spcpl.py:28,765) ----------
 // Slab r of a column covers the LES levels [k0, k1), k1 = min(max(idx[0..r]), nk), k0 likewise for r-1
 // (idx = searchsorted(zh, Zh, 'right')[:-1][::-1], spcpl.py:26,764, made monotone and clipped).
@@ -197,7 +228,8 @@ __device__ double integral_w(double a, double b, const double* z, int n, const d
 // the others are queued. Returns the queue length (after a block barrier).
 template <typename T>
 __device__ __forceinline__ int cloud_slab_queue(const int32_t* slab_idx, const int32_t* cnt, int nk, int nlev, int c,
-                                                int* kend, int* live_k, int* queue, int32_t* cntslab, T* A) {
+                                                int* kend, int* live_k, int* queue, int32_t* cntslab, T* A,
+                                                int* cs_sh = nullptr) {
   __shared__ int wmax[32];
   __shared__ int nqueue;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -232,24 +264,20 @@ __device__ __forceinline__ int cloud_slab_queue(const int32_t* slab_idx, const i
     } else {
       if (cntslab) cntslab[(size_t)c * nlev + r] = 0;
       if (A) A[(size_t)c * nlev + r] = (T)0;
+      if (cs_sh) cs_sh[r] = 0;
     }
   }
   __syncthreads();
   return nqueue;
 }
 
+// The queued (cloudy) slabs of one column, one per warp; results to global memory (cntslab / A, ascending slab
+// order) and/or to the block's shared array cs_sh (K3's fused prologue). No barrier inside.
 template <typename T>
-__global__ void __launch_bounds__(256) cloud_project_kji_kernel(const uint32_t* mask, const int32_t* slab_idx,
-                                                                const int32_t* cnt, int mw, int nk, int nlev, double npts,
-                                                                int32_t* cntslab, T* A) {
-  extern __shared__ __align__(16) double sm[];
-  int* kend = reinterpret_cast<int*>(sm);  // [nlev] exclusive end level of every slab
-  int* live_k = kend + nlev;               // [nk] 1 where the level has any cloudy cell
-  int* queue = live_k + nk;                // [nlev] slabs that need the mask
-  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int nq = cloud_slab_queue<T>(slab_idx, cnt, nk, nlev, c, kend, live_k, queue, cntslab, A);
-  const uint32_t* m = mask + (size_t)c * nk * mw;
-  const bool vec = (mw & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;   // block-uniform
+__device__ __forceinline__ void project_kji_queued(const uint32_t* m, bool vec, int mw, int nq, const int* queue,
+                                                   const int* kend, const int* live_k, int nlev, int c, double npts,
+                                                   int32_t* cntslab, T* A, int* cs_sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int qi = warp; qi < nq; qi += nwarps) {
     const int r = queue[qi];
     const int k0 = r ? kend[r - 1] : 0, k1 = kend[r];
@@ -311,8 +339,23 @@ __global__ void __launch_bounds__(256) cloud_project_kji_kernel(const uint32_t* 
     if (lane == 0) {
       if (cntslab) cntslab[(size_t)c * nlev + r] = n;
       if (A) A[(size_t)c * nlev + r] = (T)((double)n / npts);
+      if (cs_sh) cs_sh[r] = n;
     }
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cloud_project_kji_kernel(const uint32_t* mask, const int32_t* slab_idx,
+                                                                const int32_t* cnt, int mw, int nk, int nlev, double npts,
+                                                                int32_t* cntslab, T* A) {
+  extern __shared__ __align__(16) double sm[];
+  int* kend = reinterpret_cast<int*>(sm);  // [nlev] exclusive end level of every slab
+  int* live_k = kend + nlev;               // [nk] 1 where the level has any cloudy cell
+  int* queue = live_k + nk;                // [nlev] slabs that need the mask
+  const int c = blockIdx.x;
+  const int nq = cloud_slab_queue<T>(slab_idx, cnt, nk, nlev, c, kend, live_k, queue, cntslab, A);
+  const bool vec = (mw & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;   // block-uniform
+  project_kji_queued<T>(mask + (size_t)c * nk * mw, vec, mw, nq, queue, kend, live_k, nlev, c, npts, cntslab, A, nullptr);
 }
 
 // Same projection for the IJK-layout mask of K1: [S][kw] words per column, bit k%32 of word k/32
@@ -427,7 +470,7 @@ int launch_cloud_projection(spc_handle h, const uint32_t* mask, const int32_t* s
   if (layout == SPC_LAYOUT_KJI) {
     const size_t smem = ((size_t)2 * nlev + nk) * sizeof(int);
     SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "nlev=%d, nk=%d too large", nlev, nk);
-    cloud_project_kji_kernel<T><<<ncol, g_proj_threads ? g_proj_threads : (per_col / nk <= 128 ? 64 : 256), smem, st>>>(mask, slab_idx, cnt, (int)(per_col / nk), nk, nlev, npts, cntslab, A);
+    cloud_project_kji_kernel<T><<<ncol, h->proj_threads ? h->proj_threads : (per_col / nk <= 128 ? 64 : 256), smem, st>>>(mask, slab_idx, cnt, (int)(per_col / nk), nk, nlev, npts, cntslab, A);
   } else {
     const int kw = (nk + 31) / 32, S = nx * ny;
     const size_t smem_reg = ((size_t)3 * nlev + nk) * sizeof(int);
@@ -450,6 +493,27 @@ int launch_cloud_projection(spc_handle h, const uint32_t* mask, const int32_t* s
   return SPC_OK;
 }
 
+// system-scope release store / acquire load of a completion flag (peer GPU memory over NVLink or pinned host memory)
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// K3. One CTA per column:
+//   prologue  (KJI mask) the projected cloud count of every GCM slab, straight from K1's bit mask into shared memory
+//   stage     LES profiles + reversed GCM heights / pressures in shared memory
+//   levels    one thread per GCM level: bracket search, 7 interpolations (or the mass-weighted integrals), 7 tendencies,
+//             stored into the packed block and into every remote target (peer GPUs over NVLink / pinned host memory)
+//   epilogue  (sync) last CTA of the launch: signal flags, wait for the peers, advance the epoch
 template <typename T>
 __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
   extern __shared__ __align__(16) double sm[];
@@ -467,19 +531,35 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
   double* v_d = u_d + nk;
   double* rho = v_d + nk;        // [nk]   (conservative only)
   double* ZhD = rho + nk;        // [nlev+1] descending half-level heights (conservative only)
+  double* zh_s = ZhD + nlev + 1; // [nk]   LES half levels (conservative only)
+  int* cs_sh = reinterpret_cast<int*>(zh_s + nk);   // [nlev] projected cloud counts, ascending slabs (fused projection)
+  int* kend = cs_sh + nlev;      // [nlev], [nk], [nlev]: scratch of the projection prologue
+  int* live_k = kend + nlev;
+  int* queue = live_k + nk;
   __shared__ int s_start;
+  __shared__ uint32_t s_epoch;
 
   const size_t b = (size_t)c * nlev, bh = (size_t)c * (nlev + 1);
   const double zs = ld<T>(a.g.Zghalf, bh + nlev);
   const spc_gcm_tend& o = a.o;
   const size_t pfs = (size_t)ncol * nk;
+  if (a.sync && threadIdx.x == 0) s_epoch = a.sync[SPC_SYNC_EPOCH];   // only this launch's last CTA changes it, at the very end
+
+  // cloud fraction source: given A | counts projected here from the KJI mask | counts written to o.cntslab by the
+  // IJK projection kernel launched just before | none
+  const bool fused = a.project_mw > 0;
+  const bool from_global = !fused && (a.les.A == nullptr) && a.les.mask && o.cntslab;
+  if (fused) {
+    const int nq = cloud_slab_queue<T>(a.les.slab_idx, a.les.cnt, nk, nlev, c, kend, live_k, queue, o.cntslab, (T*)nullptr, cs_sh);
+    const bool vec = (a.project_mw & 3) == 0 && (reinterpret_cast<uintptr_t>(a.les.mask) & 15) == 0;
+    project_kji_queued<T>(a.les.mask + (size_t)c * nk * a.project_mw, vec, a.project_mw, nq, queue, kend, live_k, nlev, c,
+                          1.0, o.cntslab, (T*)nullptr, cs_sh);
+  }
 
   for (int l = threadIdx.x; l < nlev; l += blockDim.x) {
     ZfA[nlev - 1 - l] = (ld<T>(a.g.Zgfull, b + l) - zs) / grav;         // les.gcm_Zf, spcpl.py:198,390
     PfA[nlev - 1 - l] = ld<T>(a.g.Pfull, b + l);
   }
-  // projected cloud counts were written to o.cntslab by the projection kernel launched just before
-  const bool from_mask = (a.les.A == nullptr) && a.les.mask && o.cntslab;
   if (a.conservative)
     for (int l = threadIdx.x; l <= nlev; l += blockDim.x) ZhD[l] = (ld<T>(a.g.Zghalf, bh + l) - zs) / grav;
   for (int k = threadIdx.x; k < nk; k += blockDim.x) {
@@ -494,7 +574,10 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
     qli_d[k] = qli;
     u_d[k] = __ldg(a.les.prof + SPC_U * pfs + i);
     v_d[k] = __ldg(a.les.prof + SPC_V * pfs + i);
-    if (a.conservative) rho[k] = ld<T>(a.les.Rhobf, i);
+    if (a.conservative) {
+      rho[k] = ld<T>(a.les.Rhobf, i);
+      zh_s[k] = __ldg(a.zh + k);
+    }
   }
   __syncthreads();
 
@@ -521,58 +604,86 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
   __syncthreads();
 
   const double npts = (double)a.les.nx * (double)a.les.ny;
-  const double zh_top = a.zh ? __ldg(a.zh + nk - 1) : 0.0;
+  const double zh_top = a.conservative ? zh_s[nk - 1] : 0.0;
+  const int tb = a.sync ? (int)(s_epoch % (uint32_t)a.n_bufs) * a.n_peers : 0;   // buffer set of this launch
   for (int l = threadIdx.x; l < nlev; l += blockDim.x) {
     const size_t i = b + l;
     const int r = nlev - 1 - l;                  // ascending slab index of GCM level l
     double A_d;                                  // profile["A"][::-1], spcpl.py:404
     if (a.les.A) A_d = ld<T>(a.les.A, b + r);
-    else if (from_mask) A_d = (double)o.cntslab[b + r] / npts;   // cntslab is in ascending slab order
+    else if (fused) A_d = (double)cs_sh[r] / npts;
+    else if (from_global) A_d = (double)o.cntslab[b + r] / npts;   // cntslab is in ascending slab order
     else A_d = 0.0;
     st<T>(o.A_d, i, A_d);
     const double x = ZfA[r];                     // Zf[l]
-    double tl, qtl, qll, qlwl, qlil, ul, vl;
+    double val[7];                               // t, qt, ql, ql_water, ql_ice, u, v on GCM level l
     if (!a.conservative) {                       // spcpl.py:468-477
       const int j = upper_bound(zf, nk, x) - 1;
       if (o.bracket) o.bracket[i] = j;
-      tl = interp_at(zf, t_d, nk, x, j);
-      qtl = interp_at(zf, qt_d, nk, x, j);
-      qll = interp_at(zf, ql_d, nk, x, j);
-      qlwl = interp_at(zf, qlw_d, nk, x, j);
-      qlil = interp_at(zf, qli_d, nk, x, j);
-      ul = interp_at(zf, u_d, nk, x, j);
-      vl = interp_at(zf, v_d, nk, x, j);
+      val[0] = interp_at(zf, t_d, nk, x, j);
+      val[1] = interp_at(zf, qt_d, nk, x, j);
+      val[2] = interp_at(zf, ql_d, nk, x, j);
+      val[3] = interp_at(zf, qlw_d, nk, x, j);
+      val[4] = interp_at(zf, qli_d, nk, x, j);
+      val[5] = interp_at(zf, u_d, nk, x, j);
+      val[6] = interp_at(zf, v_d, nk, x, j);
     } else {                                     // spcpl.py:479-488 -> sputils.interp_c (sputils.py:173-189)
-      tl = qtl = qll = qlwl = qlil = ul = vl = 0.0;
+#pragma unroll
+      for (int n = 0; n < 7; ++n) val[n] = 0.0;
       if (o.bracket) o.bracket[i] = -2;
       if (ZhD[l] < zh_top) {                     // sputils.py:187
-        const double lo = ZhD[l + 1], hi = ZhD[l];
-        tl = integral_w(lo, hi, a.zh, nk, t_d, rho);
-        qtl = integral_w(lo, hi, a.zh, nk, qt_d, rho);
-        qll = integral_w(lo, hi, a.zh, nk, ql_d, rho);
-        qlwl = integral_w(lo, hi, a.zh, nk, qlw_d, rho);
-        qlil = integral_w(lo, hi, a.zh, nk, qli_d, rho);
-        ul = integral_w(lo, hi, a.zh, nk, u_d, rho);
-        vl = integral_w(lo, hi, a.zh, nk, v_d, rho);
+        const double* const q[7] = {t_d, qt_d, ql_d, qlw_d, qli_d, u_d, v_d};
+        integral_w_multi<7>(ZhD[l + 1], ZhD[l], zh_s, nk, q, rho, val);
       }
     }
     const double ft = a.dt;                      // spcpl.py:427
     double f[SPC_NTEND];
-    f[SPC_F_T] = a.factor * (tl - ld<T>(a.g.T, i)) / ft;                 // spcpl.py:518
-    f[SPC_F_SH] = a.factor * ((qtl - qll) - ld<T>(a.g.SH, i)) / ft;      // spcpl.py:519
-    f[SPC_F_QL] = a.factor * (qlwl - ld<T>(a.g.QL, i)) / ft;             // spcpl.py:520
-    f[SPC_F_QI] = a.factor * (qlil - ld<T>(a.g.QI, i)) / ft;             // spcpl.py:521
-    f[SPC_F_U] = a.factor * (ul - ld<T>(a.g.U, i)) / ft;                 // spcpl.py:524
-    f[SPC_F_V] = a.factor * (vl - ld<T>(a.g.V, i)) / ft;                 // spcpl.py:525
-    f[SPC_F_A] = a.factor * (A_d - ld<T>(a.g.A, i)) / ft;                // spcpl.py:526
+    f[SPC_F_T] = a.factor * (val[0] - ld<T>(a.g.T, i)) / ft;               // spcpl.py:518
+    f[SPC_F_SH] = a.factor * ((val[1] - val[2]) - ld<T>(a.g.SH, i)) / ft;  // spcpl.py:519
+    f[SPC_F_QL] = a.factor * (val[3] - ld<T>(a.g.QL, i)) / ft;             // spcpl.py:520
+    f[SPC_F_QI] = a.factor * (val[4] - ld<T>(a.g.QI, i)) / ft;             // spcpl.py:521
+    f[SPC_F_U] = a.factor * (val[5] - ld<T>(a.g.U, i)) / ft;               // spcpl.py:524
+    f[SPC_F_V] = a.factor * (val[6] - ld<T>(a.g.V, i)) / ft;               // spcpl.py:525
+    f[SPC_F_A] = a.factor * (A_d - ld<T>(a.g.A, i)) / ft;                  // spcpl.py:526
     const bool above = l < s_start;              // spcpl.py:527-533: f[0:start_index] *= 0
 #pragma unroll
     for (int n = 0; n < SPC_NTEND; ++n) {
       const double v = above ? f[n] * 0.0 : f[n];
       const size_t e = ((size_t)c * SPC_NTEND + n) * nlev + l;
       st<T>(o.tend, e, v);
-      for (int p = 0; p < a.n_peers; ++p) static_cast<T*>(a.peers[p])[a.peer_off + e] = (T)v;   // NVLink stores
+      for (int p = 0; p < a.n_peers; ++p) static_cast<T*>(a.peers[tb + p])[a.peer_off + e] = (T)v;   // NVLink / PCIe stores
     }
+  }
+
+  if (a.sync == nullptr) return;
+  // ---- completion protocol (include/spcpl_b200.h, spc_gcm_tend.sync) ----
+  __threadfence_system();                          // this thread's stores are visible to peers / the host
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  uint32_t last = 0;
+  if (lane == 0) last = (atomicAdd(a.sync + SPC_SYNC_DONE, 1u) == gridDim.x - 1) ? 1u : 0u;
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence_system();                          // acquire: every CTA's fenced stores precede the flags below
+  const uint32_t next = s_epoch + 1u;
+  if (lane < a.n_signal) st_release_sys(a.signal[lane] + SPC_SYNC_FLAG0 + a.sync_slot, next);
+  if (lane < a.n_wait) {
+    const uint32_t* flag = a.sync + SPC_SYNC_FLAG0 + lane;
+    const unsigned long long t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(flag) - next) < 0) {
+      __nanosleep(64);
+      if (global_ns() - t0 > 20000000000ull) {     // a peer never arrived: record it and let the launch end
+        atomicExch(a.sync + SPC_SYNC_ERROR, 1u + (uint32_t)lane);
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    a.sync[SPC_SYNC_DONE] = 0u;
+    __threadfence();
+    a.sync[SPC_SYNC_EPOCH] = next;
   }
 }
 
@@ -677,13 +788,17 @@ int check_gcm(const spc_gcm_cols* g, int couple_surface, const char* who) {
 
 extern "C" {
 
-// Tuning hook, not part of the public ABI (tools/step_probe.py only): threads per column CTA of K2 / K3.
-int spc_tune_profiles(int k2_threads, int k3_threads, int proj_threads) {
-  g_proj_threads = (proj_threads >= 32 && proj_threads <= 256) ? (proj_threads & ~31) : 0;
-  g_k2_threads = (k2_threads >= 32 && k2_threads <= kThreads) ? (k2_threads & ~31) : 0;
-  g_k3_threads = (k3_threads >= 32 && k3_threads <= kThreads) ? (k3_threads & ~31) : 0;
+#ifdef SPC_TUNING
+// Tuning hook of libspcpl_b200_tune.so (tools/step_probe.py), not part of the ABI: threads per column CTA.
+int spc_tune_profiles(spc_handle h, int k2_threads, int k3_threads, int proj_threads) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  h->proj_threads = (proj_threads >= 32 && proj_threads <= 256) ? (proj_threads & ~31) : 0;
+  h->k2_threads = (k2_threads >= 32 && k2_threads <= kThreads) ? (k2_threads & ~31) : 0;
+  h->k3_threads = (k3_threads >= 32 && k3_threads <= kThreads) ? (k3_threads & ~31) : 0;
   return SPC_OK;
 }
+#endif
 
 int spc_gcm_to_les(spc_handle h, const spc_gcm_cols* gcm, const double* zf, const double* zh, int nk,
                    const double* les_prof, const void* ps_les, double dt, double factor, int couple_surface,
@@ -708,7 +823,7 @@ int spc_gcm_to_les(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   a.o = *out;
   a.dt = dt; a.factor = factor; a.nk = nk; a.couple_surface = couple_surface;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int threads = column_threads(g_k2_threads, std::max(gcm->nlev + 1, nk));
+  const int threads = column_threads(h->k2_threads, std::max(gcm->nlev + 1, nk));
   if (gcm->dtype == SPC_F32) gcm_to_les_kernel<float><<<gcm->ncol, threads, smem, st>>>(a);
   else gcm_to_les_kernel<double><<<gcm->ncol, threads, smem, st>>>(a);
   SPC_CUDA(cudaGetLastError());
@@ -725,38 +840,63 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   SPC_REQUIRE(zf && les && out && nk >= 1, SPC_ERR_ARG, "spc_les_to_gcm: zf/les/out NULL or nk < 1");
   SPC_REQUIRE(dt != 0.0, SPC_ERR_ARG, "spc_les_to_gcm: dt must be non-zero");
   SPC_REQUIRE(out->tend != nullptr, SPC_ERR_ARG, "spc_les_to_gcm: out->tend is NULL");
-  SPC_REQUIRE(out->n_peers >= 0 && out->n_peers <= SPC_MAX_PEERS && out->peer_col0 >= 0, SPC_ERR_ARG,
+  const int n_peers = out->tend_peers ? out->n_peers : 0;
+  const int n_bufs = out->sync ? out->n_bufs : 1;
+  SPC_REQUIRE(n_peers >= 0 && n_peers <= SPC_MAX_PEERS && out->peer_col0 >= 0, SPC_ERR_ARG,
               "spc_les_to_gcm: n_peers=%d / peer_col0=%d out of range", out->n_peers, out->peer_col0);
-  for (int p = 0; out->tend_peers && p < out->n_peers; ++p)
+  SPC_REQUIRE(n_bufs == 1 || n_bufs == 2, SPC_ERR_ARG, "spc_les_to_gcm: n_bufs=%d (1 or 2)", out->n_bufs);
+  for (int p = 0; p < n_peers * n_bufs; ++p)
     SPC_REQUIRE(out->tend_peers[p] != nullptr, SPC_ERR_ARG, "spc_les_to_gcm: tend_peers[%d] is NULL", p);
+  if (out->sync) {
+    SPC_REQUIRE(out->n_signal >= 0 && out->n_signal <= SPC_MAX_PEERS + 1 && (out->n_signal == 0 || out->signal), SPC_ERR_ARG,
+                "spc_les_to_gcm: n_signal=%d out of range or signal is NULL", out->n_signal);
+    SPC_REQUIRE(out->n_wait >= 0 && out->n_wait <= SPC_SYNC_MAX_SLOTS && out->sync_slot >= 0 && out->sync_slot < SPC_SYNC_MAX_SLOTS,
+                SPC_ERR_ARG, "spc_les_to_gcm: n_wait=%d / sync_slot=%d out of range", out->n_wait, out->sync_slot);
+    for (int p = 0; p < out->n_signal; ++p)
+      SPC_REQUIRE(out->signal[p] != nullptr, SPC_ERR_ARG, "spc_les_to_gcm: signal[%d] is NULL", p);
+  }
   SPC_REQUIRE(les->prof && les->QL_ice && les->T, SPC_ERR_ARG, "spc_les_to_gcm: a LES profile pointer is NULL");
   SPC_REQUIRE(!(conservative && (!les->Rhobf || !zh)), SPC_ERR_ARG,
               "spc_les_to_gcm: conservative coarsening needs Rhobf and zh");
   const bool project = !les->A && les->mask;
+  size_t mask_words = 0;
   if (project) {
     SPC_REQUIRE(les->slab_idx != nullptr, SPC_ERR_ARG, "spc_les_to_gcm: mask given without slab_idx");
     SPC_REQUIRE(les->nx > 0 && les->ny > 0, SPC_ERR_ARG, "spc_les_to_gcm: mask given without nx, ny");
-    SPC_REQUIRE(out->cntslab != nullptr, SPC_ERR_ARG,
-                "spc_les_to_gcm: out->cntslab is required when the cloud fraction comes from the mask");
+    mask_words = spc_mask_words_per_column(les->vol_dtype, les->layout, les->nx, les->ny, nk);
+    SPC_REQUIRE(mask_words > 0, SPC_ERR_UNSUPPORTED, "spc_les_to_gcm: no cloud mask format for this layout/shape");
+    SPC_REQUIRE(les->layout == SPC_LAYOUT_KJI || out->cntslab != nullptr, SPC_ERR_ARG,
+                "spc_les_to_gcm: out->cntslab is required when the cloud fraction comes from an IJK-layout mask");
   }
+  SPC_REQUIRE(!(out->sync && gcm->ncol == 0), SPC_ERR_ARG, "spc_les_to_gcm: the completion protocol needs at least one column per rank");
   if (gcm->ncol == 0) return SPC_OK;
-  const size_t smem = ((size_t)2 * gcm->nlev + (size_t)9 * nk + gcm->nlev + 1) * sizeof(double);
+  // doubles: ZfA, PfA [nlev] | zf + 7 profiles + rho [9 nk] | ZhD [nlev+1] | zh [nk];  ints: cs, kend, queue [nlev], live_k [nk]
+  const size_t smem = ((size_t)3 * gcm->nlev + 1 + (size_t)10 * nk) * sizeof(double) + ((size_t)3 * gcm->nlev + nk) * sizeof(int);
   SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_les_to_gcm: nlev=%d, nk=%d too large", gcm->nlev, nk);
   spc::DeviceGuard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (project) {  // projected cloud counts per GCM slab, consumed by the tendency kernel right after
+  K3Args a;
+  a.project_mw = 0;
+  if (project && les->layout == SPC_LAYOUT_KJI) {
+    a.project_mw = (int)(mask_words / nk);       // the projection is K3's own prologue
+  } else if (project) {                          // IJK mask: its projection kernel feeds K3 through out->cntslab
     rc = launch_cloud_projection<float>(h, les->mask, les->slab_idx, les->cnt, les->vol_dtype, les->layout, les->nx, les->ny,
                                         nk, gcm->ncol, gcm->nlev, out->cntslab, nullptr, st);
     if (rc) return rc;
   }
-  K3Args a;
   a.g = to_ptrs(gcm);
   a.zf = zf; a.zh = zh; a.les = *les; a.o = *out;
   a.dt = dt; a.factor = factor; a.nk = nk; a.conservative = conservative;
-  a.n_peers = out->tend_peers ? out->n_peers : 0;
-  for (int p = 0; p < a.n_peers; ++p) a.peers[p] = out->tend_peers[p];
+  a.n_peers = n_peers;
+  a.n_bufs = n_bufs;
+  for (int p = 0; p < n_peers * n_bufs; ++p) a.peers[p] = out->tend_peers[p];
   a.peer_off = (size_t)out->peer_col0 * SPC_NTEND * gcm->nlev;
-  const int threads = column_threads(g_k3_threads, std::max(gcm->nlev + 1, nk));
+  a.sync = out->sync;
+  a.n_signal = out->sync ? out->n_signal : 0;
+  a.n_wait = out->sync ? out->n_wait : 0;
+  a.sync_slot = out->sync_slot;
+  for (int p = 0; p < a.n_signal; ++p) a.signal[p] = out->signal[p];
+  const int threads = column_threads(h->k3_threads, std::max(gcm->nlev + 1, nk));
   if (gcm->dtype == SPC_F32) les_to_gcm_kernel<float><<<gcm->ncol, threads, smem, st>>>(a);
   else les_to_gcm_kernel<double><<<gcm->ncol, threads, smem, st>>>(a);
   SPC_CUDA(cudaGetLastError());

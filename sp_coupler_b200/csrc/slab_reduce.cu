@@ -36,7 +36,6 @@ struct Ring {
 };
 constexpr int kSubBytes = 4096;
 constexpr uint32_t kFull = 0xffffffffu;
-int g_k1_variant = 0;  // tuning hook (spc_tune_k1); 0 = production default
 
 struct K1Args {
   const void *v0, *v1, *v2, *v3, *v4;  // THL,QT,QL,U,V (named members: no local-memory copy for vol[f])
@@ -90,7 +89,7 @@ __device__ __forceinline__ uint64_t l2_evict_last_policy() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ void tma_bulk_g2s_nohint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+__device__ __forceinline__ __attribute__((unused)) void tma_bulk_g2s_nohint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar)
                : "memory");
@@ -802,130 +801,154 @@ bool fast_path(int dtype, long long S) {
   return slab_bytes % 16 == 0 && slab_bytes >= 1024;
 }
 
-template <typename T, typename R>
-int launch_tma(spc_handle h, const K1Args& a, cudaStream_t st) {
-  const size_t smem = (size_t)R::kWarps * R::kStages * R::kChunk + (size_t)R::kWarps * R::kStages * 8;
-  static thread_local int configured_dev = -1;
-  if (configured_dev != h->device) {
-    SPC_CUDA(cudaFuncSetAttribute(slab_reduce_tma_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_dev = h->device;
-  }
-  const long long want = (a.total + R::kWarps - 1) / R::kWarps;
-  const int grid = (int)std::min<long long>(h->num_sms, std::max<long long>(want, 1));
-  slab_reduce_tma_kernel<T, R><<<grid, R::kWarps * 32, smem, st>>>(a);
-  return SPC_OK;
-}
-
 // Ring shapes. Production picks by slab size and element type (round-1 sweeps on B200, profiles/README.md): with the
 // evict_normal L2 policy 96-128 KB in flight per SM in single-stage per-warp rings is the sweet spot - deeper rings
 // (192 KB) cost 6-8 % of bandwidth, fewer than 8 warps cannot keep up with the float32->float64 conversions.
 //   slab >= 8 KB : float32 16 warps x 1 x 8 KB, float64 12 warps x 1 x 8 KB
 //   slab  = 4 KB : pairs of slabs, 12 warps x 1 x 8 KB (slab_reduce_tma_pair_kernel)     other slab < 8 KB : 24 warps x 1 x 4 KB
-// Variants 1.. exist for tools/k1_probe.py (spc_tune_k1) and document the sweep.
+using RingF32 = Ring<16, 8192, 1, false, 1, 1>;
+using RingF64 = Ring<12, 8192, 1, false, 1, 1>;
+using RingSmall = Ring<24, 4096, 1, false, 1, 1>;
+constexpr int kPairWarps = 12;
+
+template <typename R>
+constexpr size_t tma_smem() {
+  return (size_t)R::kWarps * R::kStages * R::kChunk + (size_t)R::kWarps * R::kStages * 8;
+}
+template <typename T, typename R>
+int configure_tma() {
+  SPC_CUDA(cudaFuncSetAttribute(slab_reduce_tma_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem<R>()));
+  return SPC_OK;
+}
+template <typename T, typename R>
+int launch_tma(spc_handle h, const K1Args& a, cudaStream_t st) {
+  const long long want = (a.total + R::kWarps - 1) / R::kWarps;
+  const int grid = (int)std::min<long long>(h->num_sms, std::max<long long>(want, 1));
+  slab_reduce_tma_kernel<T, R><<<grid, R::kWarps * 32, tma_smem<R>(), st>>>(a);
+  return SPC_OK;
+}
+
+template <int W>
+constexpr size_t pair_smem() {
+  return (size_t)W * 2 * kSubBytes + (size_t)W * 8;
+}
+template <typename T, int W>
+int configure_tma_pair() {
+  SPC_CUDA(cudaFuncSetAttribute(slab_reduce_tma_pair_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem<W>()));
+  return SPC_OK;
+}
+template <typename T, int W>
+int launch_tma_pair(spc_handle h, const K1Args& a, cudaStream_t st) {
+  const long long want = ((a.total >> 1) + W - 1) / W;
+  const int grid = (int)std::min<long long>(h->num_sms, std::max<long long>(want, 1));
+  slab_reduce_tma_pair_kernel<T, W><<<grid, W * 32, pair_smem<W>(), st>>>(a);
+  return SPC_OK;
+}
+
+#ifdef SPC_TUNING
+// Sweep variants of libspcpl_b200_tune.so (tools/k1_probe.py, spc_tune_k1); they document the round-1 sweeps and are
+// not compiled into the production library. X(id, warps, chunk, stages, blocked); Y adds (L2 hint, sub-blocks per trip):
+// hint 0 = evict_first, 1 = evict_normal (production), 2 = no cache hint, 3 = evict_last.
 #define SPC_K1_VARIANTS(X)                                                               \
   X(1, 12, 8192, 1, false) X(2, 24, 4096, 1, false) X(3, 16, 4096, 3, false) X(4, 8, 8192, 2, false) \
   X(5, 8, 16384, 1, false) X(6, 16, 4096, 2, false) X(7, 12, 8192, 2, false) X(8, 12, 8192, 1, true)
-// extra probes of the production shape: L2 policy of the copies (10 = evict_first, 12 = no cache hint, 14 = evict_last; production is
-// evict_normal: +0.7 % float32, +4.5 % float64, +1.9 % at 256 KB slabs over evict_first) and 11 = both sub-blocks of a chunk per trip
 #define SPC_K1_VARIANTS2(Y) Y(10, 12, 8192, 1, false, 0, 1) Y(11, 12, 8192, 1, false, 1, 2) Y(12, 12, 8192, 1, false, 2, 1) \
   Y(14, 12, 8192, 1, false, 3, 1) Y(15, 24, 4096, 1, false, 0, 1) \
   Y(16, 8, 8192, 3, false, 1, 1) Y(17, 8, 8192, 2, false, 1, 2) Y(18, 8, 8192, 2, false, 2, 1) Y(19, 16, 8192, 1, false, 1, 1) \
   Y(20, 8, 8192, 2, false, 0, 1) Y(21, 6, 16384, 2, false, 1, 1)
+#endif
 
-template <typename T, int W>
-int launch_tma_pair(spc_handle h, const K1Args& a, cudaStream_t st) {
-  const size_t smem = (size_t)W * 2 * kSubBytes + (size_t)W * 8;
-  static thread_local int configured_dev = -1;
-  if (configured_dev != h->device) {
-    SPC_CUDA(cudaFuncSetAttribute(slab_reduce_tma_pair_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_dev = h->device;
-  }
-  const long long want = ((a.total >> 1) + W - 1) / W;
-  const int grid = (int)std::min<long long>(h->num_sms, std::max<long long>(want, 1));
-  slab_reduce_tma_pair_kernel<T, W><<<grid, W * 32, smem, st>>>(a);
-  return SPC_OK;
-}
-
-int k1_variant_for(int slab_bytes, int esize) {
-  if (g_k1_variant != 0) return g_k1_variant;
-  if (slab_bytes < 8192) return 2;
-  return esize == 4 ? 19 : 1;   // float32 needs more warps for the conversions: 16 x 1 x 8 KB; float64: 12 x 1 x 8 KB
-}
-
-int k1_chunk_bytes(int slab_bytes, int esize) {
-  switch (k1_variant_for(slab_bytes, esize)) {
+// chunk bytes of the ring that will serve this slab size / element type
+int k1_chunk_bytes(spc_handle h, int slab_bytes, int esize) {
+#ifdef SPC_TUNING
+  switch (h->k1_variant) {
 #define X(id, w, c, s, b) case id: return c;
     SPC_K1_VARIANTS(X)
 #undef X
 #define Y(id, w, c, s, b, hint, un) case id: return c;
     SPC_K1_VARIANTS2(Y)
 #undef Y
-    default: return 4096;
+    default: break;
   }
+#endif
+  (void)h; (void)esize;
+  return slab_bytes < 8192 ? 4096 : 8192;
 }
 
 template <typename T>
 int launch_kji(spc_handle h, const K1Args& a, bool fast, cudaStream_t st) {
-  if (fast && a.slab_bytes == kSubBytes && a.per_field % 2 == 0 && (g_k1_variant == 0 || g_k1_variant == 9 || g_k1_variant == 22)) {
-    // 4 KB slabs in pairs (variant 9 = 12 warps, 22 = 16 warps; 2 = one slab per copy)
-    const int rc = g_k1_variant == 22 ? launch_tma_pair<T, 16>(h, a, st) : launch_tma_pair<T, 12>(h, a, st);
-    if (rc) return rc;
-  } else if (fast) {
-    int rc;
-    switch (k1_variant_for(a.slab_bytes, (int)sizeof(T))) {
+  int rc = SPC_OK;
+  if (!fast) {
+    const long long want = (a.total + 7) / 8;
+    const int grid = (int)std::min<long long>((long long)h->num_sms * 8, std::max<long long>(want, 1));
+    slab_reduce_generic_kernel<T><<<grid, 256, 0, st>>>(a);
+  } else
+#ifdef SPC_TUNING
+  if (h->k1_variant != 0 && !(a.slab_bytes == kSubBytes && a.per_field % 2 == 0 && (h->k1_variant == 9 || h->k1_variant == 22))) {
+    switch (h->k1_variant) {
 #define X(id, w, c, s, b) case id: rc = launch_tma<T, Ring<w, c, s, b>>(h, a, st); break;
       SPC_K1_VARIANTS(X)
 #undef X
 #define Y(id, w, c, s, b, hint, un) case id: rc = launch_tma<T, Ring<w, c, s, b, hint, un>>(h, a, st); break;
       SPC_K1_VARIANTS2(Y)
 #undef Y
-      default: rc = SPC_ERR_ARG; spc::set_error("unknown K1 variant %d", g_k1_variant); break;
+      default: rc = SPC_ERR_ARG; spc::set_error("unknown K1 variant %d", h->k1_variant); break;
     }
-    if (rc) return rc;
+  } else if (h->k1_variant == 22) {
+    rc = launch_tma_pair<T, 16>(h, a, st);
+  } else
+#endif
+  if (a.slab_bytes == kSubBytes && a.per_field % 2 == 0) {
+    rc = launch_tma_pair<T, kPairWarps>(h, a, st);          // 4 KB slabs in pairs
+  } else if (a.slab_bytes < 8192) {
+    rc = launch_tma<T, RingSmall>(h, a, st);
   } else {
-    const long long want = (a.total + 7) / 8;
-    const int grid = (int)std::min<long long>((long long)h->num_sms * 8, std::max<long long>(want, 1));
-    slab_reduce_generic_kernel<T><<<grid, 256, 0, st>>>(a);
+    rc = launch_tma<T, std::conditional_t<sizeof(T) == 4, RingF32, RingF64>>(h, a, st);
   }
+  if (rc) return rc;
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
 }
 
-int g_ijk_variant = 0;  // tuning hook (spc_tune_k1 with 100 + id): 0 = TMA path when eligible, 1 = always the CTA-per-item kernel
+using IjkProd = IjkRing<12, 8192, 2>;
 
 template <typename T, int SLOTS, typename R>
-int launch_ijk_tma(spc_handle h, const K1Args& a, IjkArgs g, cudaStream_t st) {
+constexpr size_t ijk_smem() {
   constexpr int VEC = 16 / (int)sizeof(T), P = SLOTS * 32;
+  return (size_t)R::kWarps * R::kChunk + (size_t)R::kWarps * P * VEC * (sizeof(double) + sizeof(int)) + (size_t)R::kWarps * 8 + 16;
+}
+template <typename T, int SLOTS, typename R>
+int configure_ijk_tma() {
+  SPC_CUDA(cudaFuncSetAttribute(slab_reduce_ijk_tma_kernel<T, SLOTS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)ijk_smem<T, SLOTS, R>()));
+  return SPC_OK;
+}
+template <typename T, int SLOTS, typename R>
+int launch_ijk_tma(spc_handle h, const K1Args& a, IjkArgs g, cudaStream_t st) {
+  constexpr int P = SLOTS * 32;
   static_assert(P * 16 <= R::kChunk, "a period must fit one ring stage");
   g.chunk_bytes = (R::kChunk / (P * 16)) * (P * 16);
   g.nch = (int)((g.item_bytes + g.chunk_bytes - 1) / g.chunk_bytes);
-  const size_t smem = (size_t)R::kWarps * R::kChunk + (size_t)R::kWarps * P * VEC * (sizeof(double) + sizeof(int)) +
-                      (size_t)R::kWarps * 8 + 16;
-  static thread_local int configured_dev = -1;
-  if (configured_dev != h->device) {
-    SPC_CUDA(cudaFuncSetAttribute(slab_reduce_ijk_tma_kernel<T, SLOTS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_dev = h->device;
-  }
   const int grid = (int)std::min<long long>(h->num_sms, g.nitems);
-  slab_reduce_ijk_tma_kernel<T, SLOTS, R><<<grid, R::kWarps * 32, smem, st>>>(a, g);
+  slab_reduce_ijk_tma_kernel<T, SLOTS, R><<<grid, R::kWarps * 32, ijk_smem<T, SLOTS, R>(), st>>>(a, g);
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
 }
 
 template <typename T, int SLOTS>
 int launch_ijk_tma_variant(spc_handle h, const K1Args& a, const IjkArgs& g, cudaStream_t st) {
-  switch (g_ijk_variant) {
-    case 2: return launch_ijk_tma<T, SLOTS, IjkRing<12, 8192, 1>>(h, a, g, st);
-    default: return launch_ijk_tma<T, SLOTS, IjkRing<12, 8192, 2>>(h, a, g, st);
-  }
+#ifdef SPC_TUNING
+  if (h->ijk_variant == 2) return launch_ijk_tma<T, SLOTS, IjkRing<12, 8192, 1>>(h, a, g, st);
+#endif
+  return launch_ijk_tma<T, SLOTS, IjkProd>(h, a, g, st);
 }
 
 // Eligibility of the IJK TMA path: whole 16-byte vectors per point, a period of at most 5 x 32 vectors,
 // whole periods per item, 16-byte aligned volumes, and (for the per-point mask) nk a multiple of 32.
 template <typename T>
-bool ijk_tma_plan(const K1Args& a, int ncol, int nk, IjkArgs& g, int& slots) {
+bool ijk_tma_plan(spc_handle h, const K1Args& a, int ncol, int nk, IjkArgs& g, int& slots) {
   constexpr int V = 16 / (int)sizeof(T);
-  if (g_ijk_variant == 1 || nk % V != 0) return false;
+  if (h->ijk_variant == 1 || nk % V != 0) return false;   // ijk_variant 1 (tuning build only): always the CTA-per-item kernel
   const int nkv = nk / V;
   int gcd = nkv, b = 32;
   while (b) { const int t = gcd % b; gcd = b; b = t; }
@@ -948,7 +971,7 @@ int launch_ijk(spc_handle h, const K1Args& a, int ncol, int nk, cudaStream_t st)
   constexpr int V = 16 / sizeof(T);
   IjkArgs g;
   int slots = 0;
-  if (ijk_tma_plan<T>(a, ncol, nk, g, slots)) {
+  if (ijk_tma_plan<T>(h, a, ncol, nk, g, slots)) {
     switch (slots) {
       case 1: return launch_ijk_tma_variant<T, 1>(h, a, g, st);
       case 2: return launch_ijk_tma_variant<T, 2>(h, a, g, st);
@@ -981,16 +1004,56 @@ int launch_ijk(spc_handle h, const K1Args& a, int ncol, int nk, cudaStream_t st)
   return SPC_OK;
 }
 
+template <typename T>
+int configure_all() {
+  int rc = SPC_OK;
+  if ((rc = configure_tma<T, RingF32>())) return rc;
+  if ((rc = configure_tma<T, RingF64>())) return rc;
+  if ((rc = configure_tma<T, RingSmall>())) return rc;
+  if ((rc = configure_tma_pair<T, kPairWarps>())) return rc;
+  if ((rc = configure_ijk_tma<T, 1, IjkProd>())) return rc;
+  if ((rc = configure_ijk_tma<T, 2, IjkProd>())) return rc;
+  if ((rc = configure_ijk_tma<T, 3, IjkProd>())) return rc;
+  if ((rc = configure_ijk_tma<T, 4, IjkProd>())) return rc;
+  if ((rc = configure_ijk_tma<T, 5, IjkProd>())) return rc;
+#ifdef SPC_TUNING
+#define X(id, w, c, s, b) if ((rc = configure_tma<T, Ring<w, c, s, b>>())) return rc;
+  SPC_K1_VARIANTS(X)
+#undef X
+#define Y(id, w, c, s, b, hint, un) if ((rc = configure_tma<T, Ring<w, c, s, b, hint, un>>())) return rc;
+  SPC_K1_VARIANTS2(Y)
+#undef Y
+  if ((rc = configure_tma_pair<T, 16>())) return rc;
+  if ((rc = configure_ijk_tma<T, 1, IjkRing<12, 8192, 1>>())) return rc;
+  if ((rc = configure_ijk_tma<T, 2, IjkRing<12, 8192, 1>>())) return rc;
+  if ((rc = configure_ijk_tma<T, 3, IjkRing<12, 8192, 1>>())) return rc;
+  if ((rc = configure_ijk_tma<T, 4, IjkRing<12, 8192, 1>>())) return rc;
+  if ((rc = configure_ijk_tma<T, 5, IjkRing<12, 8192, 1>>())) return rc;
+#endif
+  return rc;
+}
+
 }  // namespace
+
+// Called once per handle (spc_create, on the handle's device): every streaming kernel of this file is opted in to its
+// dynamic shared memory there, so the launch paths carry no lazily initialised state and are re-entrant.
+int spc::k1_configure(spc_ctx*) {
+  const int rc = configure_all<float>();
+  return rc ? rc : configure_all<double>();
+}
 
 extern "C" {
 
-// Tuning hook, not part of the public ABI (tools/k1_probe.py only): selects the TMA ring shape.
-int spc_tune_k1(int variant) {
-  if (variant >= 100) g_ijk_variant = variant - 100;
-  else g_k1_variant = variant;
+#ifdef SPC_TUNING
+// Tuning hook of libspcpl_b200_tune.so (tools/k1_probe.py), not part of the ABI: selects the TMA ring shape of this handle.
+int spc_tune_k1(spc_handle h, int variant) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  if (variant >= 100) h->ijk_variant = variant - 100;
+  else h->k1_variant = variant;
   return SPC_OK;
 }
+#endif
 
 size_t spc_mask_words_per_column(int dtype, int layout, int nx, int ny, int nk) {
   if (nx <= 0 || ny <= 0 || nk <= 0 || (layout != SPC_LAYOUT_KJI && layout != SPC_LAYOUT_IJK)) return 0;
@@ -1027,7 +1090,7 @@ int spc_slab_reduce(spc_handle h, const void* const vol[5], int dtype, int layou
   a.total = a.per_field * SPC_NFIELDS;
   a.S = (int)S;
   a.slab_bytes = (int)(S * (dtype == SPC_F32 ? 4 : 8));
-  const int chunk = k1_chunk_bytes(a.slab_bytes, dtype == SPC_F32 ? 4 : 8);
+  const int chunk = k1_chunk_bytes(h, a.slab_bytes, dtype == SPC_F32 ? 4 : 8);
   a.nch = (a.slab_bytes + chunk - 1) / chunk;
   a.nsub = (a.slab_bytes + kSubBytes - 1) / kSubBytes;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -52,6 +52,15 @@ int spc_create(spc_handle* out, int device) {
   c->num_sms = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   c->magic = SPC_MAGIC;
+  c->k1_variant = c->ijk_variant = c->k2_threads = c->k3_threads = c->proj_threads = 0;
+  {
+    spc::DeviceGuard guard(device);
+    const int rc = spc::k1_configure(c);
+    if (rc) {
+      delete c;
+      return rc;
+    }
+  }
   *out = c;
   return SPC_OK;
 }
@@ -61,6 +70,38 @@ int spc_destroy(spc_handle h) {
   if (rc) return rc;
   h->magic = 0;
   delete h;
+  return SPC_OK;
+}
+
+int spc_host_register(spc_handle h, void* p, size_t nbytes, void** dev_ptr) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  SPC_REQUIRE(p != nullptr && nbytes > 0 && dev_ptr != nullptr, SPC_ERR_ARG, "spc_host_register: NULL pointer or empty range");
+  spc::DeviceGuard guard(h->device);
+  SPC_CUDA(cudaHostRegister(p, nbytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+  cudaError_t e = cudaHostGetDevicePointer(dev_ptr, p, 0);
+  if (e != cudaSuccess) {
+    cudaHostUnregister(p);
+    return spc::cuda_fail(e, "cudaHostGetDevicePointer");
+  }
+  return SPC_OK;
+}
+
+int spc_host_unregister(spc_handle h, void* p) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  SPC_REQUIRE(p != nullptr, SPC_ERR_ARG, "spc_host_unregister: NULL pointer");
+  spc::DeviceGuard guard(h->device);
+  SPC_CUDA(cudaHostUnregister(p));
+  return SPC_OK;
+}
+
+int spc_host_device_pointer(spc_handle h, void* p, void** dev_ptr) {
+  int rc = spc::check_handle(h);
+  if (rc) return rc;
+  SPC_REQUIRE(p != nullptr && dev_ptr != nullptr, SPC_ERR_ARG, "spc_host_device_pointer: NULL pointer");
+  spc::DeviceGuard guard(h->device);
+  SPC_CUDA(cudaHostGetDevicePointer(dev_ptr, p, 0));
   return SPC_OK;
 }
 

@@ -12,6 +12,8 @@ struct spc_ctx {
   int num_sms;
   int max_smem_optin;
   uint32_t magic;
+  // tuning overrides; always 0 (= production choice) unless set through libspcpl_b200_tune.so (-DSPC_TUNING)
+  int k1_variant, ijk_variant, k2_threads, k3_threads, proj_threads;
 };
 #define SPC_MAGIC 0x53504342u
 
@@ -26,6 +28,7 @@ constexpr double rlv = 2.53e6;
 constexpr double grav = 9.81;
 
 void set_error(const char* fmt, ...);
+int k1_configure(spc_ctx* c);   // slab_reduce.cu: opt the streaming kernels in to their dynamic shared memory on c->device
 int check_handle(spc_handle h);
 int cuda_fail(cudaError_t e, const char* what);
 

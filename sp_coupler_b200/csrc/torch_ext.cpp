@@ -41,15 +41,27 @@ const void* cptr(const at::Tensor& t, const c10::Device& dev, const char* name) 
   return t.data_ptr();
 }
 
-void* opt(const TDict& d, const char* key, const c10::Device& dev) {
+// Optional tensor of a dict: device, contiguity, dtype and element count are all checked, because the C ABI behind
+// takes raw pointers and a buffer of the wrong type or length would be written out of bounds on the device.
+void* opt(const TDict& d, const char* key, const c10::Device& dev, at::ScalarType st, int64_t numel) {
   if (!d.contains(key)) return nullptr;
-  return const_cast<void*>(cptr(d.at(key), dev, key));
+  const at::Tensor& t = d.at(key);
+  TORCH_CHECK(t.scalar_type() == st, key, " must be ", st, ", got ", t.scalar_type());
+  TORCH_CHECK(t.numel() == numel, key, " must have ", numel, " elements, got ", t.numel());
+  return const_cast<void*>(cptr(t, dev, key));
+}
+const void* opt_t(const c10::optional<at::Tensor>& t, const char* name, const c10::Device& dev, at::ScalarType st, int64_t numel) {
+  if (!t.has_value()) return nullptr;
+  TORCH_CHECK(t->scalar_type() == st, name, " must be ", st, ", got ", t->scalar_type());
+  TORCH_CHECK(t->numel() == numel, name, " must have ", numel, " elements, got ", t->numel());
+  return cptr(*t, dev, name);
 }
 
-const void* req(const TDict& d, const char* key, const c10::Device& dev, at::ScalarType st) {
+const void* req(const TDict& d, const char* key, const c10::Device& dev, at::ScalarType st, int64_t numel) {
   TORCH_CHECK(d.contains(key), "missing GCM/LES field '", key, "'");
   const at::Tensor& t = d.at(key);
   TORCH_CHECK(t.scalar_type() == st, key, " has the wrong dtype");
+  TORCH_CHECK(t.numel() == numel, key, " must have ", numel, " elements, got ", t.numel());
   return cptr(t, dev, key);
 }
 
@@ -63,14 +75,15 @@ spc_gcm_cols gcm_struct(const TDict& g, const c10::Device& dev, bool surface) {
   s.ncol = (int)T.size(0);
   s.nlev = (int)T.size(1);
   s.dtype = dtype_code(T);
-  s.U = req(g, "U", dev, st); s.V = req(g, "V", dev, st); s.T = req(g, "T", dev, st); s.SH = req(g, "SH", dev, st);
-  s.QL = req(g, "QL", dev, st); s.QI = req(g, "QI", dev, st); s.Pfull = req(g, "Pfull", dev, st);
-  s.A = req(g, "A", dev, st); s.Zgfull = req(g, "Zgfull", dev, st);
-  s.Phalf = req(g, "Phalf", dev, st); s.Zghalf = req(g, "Zghalf", dev, st);
+  const int64_t nf = (int64_t)s.ncol * s.nlev, nh = (int64_t)s.ncol * (s.nlev + 1), nc = s.ncol;
+  s.U = req(g, "U", dev, st, nf); s.V = req(g, "V", dev, st, nf); s.T = req(g, "T", dev, st, nf); s.SH = req(g, "SH", dev, st, nf);
+  s.QL = req(g, "QL", dev, st, nf); s.QI = req(g, "QI", dev, st, nf); s.Pfull = req(g, "Pfull", dev, st, nf);
+  s.A = req(g, "A", dev, st, nf); s.Zgfull = req(g, "Zgfull", dev, st, nf);
+  s.Phalf = req(g, "Phalf", dev, st, nh); s.Zghalf = req(g, "Zghalf", dev, st, nh);
   if (surface) {
-    s.Z0M = req(g, "Z0M", dev, st); s.Z0H = req(g, "Z0H", dev, st); s.QLflux = req(g, "QLflux", dev, st);
-    s.QIflux = req(g, "QIflux", dev, st); s.SHflux = req(g, "SHflux", dev, st); s.TSflux = req(g, "TSflux", dev, st);
-    s.TLflux = opt(g, "TLflux", dev);
+    s.Z0M = req(g, "Z0M", dev, st, nc); s.Z0H = req(g, "Z0H", dev, st, nc); s.QLflux = req(g, "QLflux", dev, st, nc);
+    s.QIflux = req(g, "QIflux", dev, st, nc); s.SHflux = req(g, "SHflux", dev, st, nc); s.TSflux = req(g, "TSflux", dev, st, nc);
+    s.TLflux = opt(g, "TLflux", dev, st, nc);
   }
   return s;
 }
@@ -80,7 +93,7 @@ int64_t mask_words_per_column(int64_t dtype, int64_t layout, int64_t nx, int64_t
 }
 
 // K1 (spcpl.py:747-759,765)
-void slab_reduce(at::TensorList vols, int64_t layout, double ql_thresh, at::Tensor prof, const c10::optional<at::Tensor>& cnt,
+void slab_reduce(at::TensorList vols, int64_t layout, double ql_thresh, at::Tensor& prof, const c10::optional<at::Tensor>& cnt,
                  const c10::optional<at::Tensor>& mask) {
   TORCH_CHECK(vols.size() == 5, "slab_reduce expects the five volumes THL, QT, QL, U, V");
   const at::Tensor& v0 = vols[0];
@@ -96,11 +109,14 @@ void slab_reduce(at::TensorList vols, int64_t layout, double ql_thresh, at::Tens
     TORCH_CHECK(vols[f].sizes() == v0.sizes() && vols[f].scalar_type() == v0.scalar_type(), "volume shapes/dtypes differ");
     p[f] = cptr(vols[f], dev, "vol");
   }
+  TORCH_CHECK(layout == SPC_LAYOUT_KJI || layout == SPC_LAYOUT_IJK, "bad layout ", layout);
   TORCH_CHECK(prof.scalar_type() == at::kDouble && prof.numel() == (int64_t)5 * ncol * nk, "prof must be float64 [5,ncol,nk]");
+  const int64_t mwords = (int64_t)ncol * (int64_t)spc_mask_words_per_column(dtype_code(v0), (int)layout, nx, ny, nk);
+  TORCH_CHECK(!mask.has_value() || mwords > 0, "no cloud-mask format for this layout / shape");
   check_rc(spc_slab_reduce(handle_for(dev.index()), p, dtype_code(v0), (int)layout, ncol, nx, ny, nk, ql_thresh,
                            (double*)cptr(prof, dev, "prof"),
-                           cnt.has_value() ? (int32_t*)cptr(*cnt, dev, "cnt") : nullptr,
-                           mask.has_value() ? (uint32_t*)cptr(*mask, dev, "mask") : nullptr,
+                           (int32_t*)opt_t(cnt, "cnt", dev, at::kInt, (int64_t)ncol * nk),
+                           (uint32_t*)opt_t(mask, "mask", dev, at::kInt, mwords),
                            at::cuda::getCurrentCUDAStream(dev.index()).stream()),
            "spc_slab_reduce");
 }
@@ -113,20 +129,26 @@ void gcm_to_les(const TDict& gcm, const at::Tensor& zf, const c10::optional<at::
   TORCH_CHECK(dev.is_cuda() && zf.scalar_type() == at::kDouble, "zf must be a float64 CUDA tensor");
   c10::cuda::CUDAGuard guard(dev);
   spc_gcm_cols g = gcm_struct(gcm, dev, couple_surface);
+  const at::ScalarType st = gcm.at("T").scalar_type();
+  const int64_t nk = zf.numel(), ck = (int64_t)g.ncol * nk, cl = (int64_t)g.ncol * g.nlev, nc = g.ncol;
   spc_les_forcing o{};
-  o.f_u = opt(out, "f_u", dev); o.f_v = opt(out, "f_v", dev); o.f_thl = opt(out, "f_thl", dev);
-  o.f_qt = opt(out, "f_qt", dev); o.f_ql = opt(out, "f_ql", dev); o.ql_ref = opt(out, "ql_ref", dev);
-  o.u = opt(out, "u", dev); o.v = opt(out, "v", dev); o.thl = opt(out, "thl", dev); o.qt = opt(out, "qt", dev);
-  o.f_ps = opt(out, "f_ps", dev); o.ps = opt(out, "ps", dev);
-  o.z0m = opt(out, "z0m", dev); o.z0h = opt(out, "z0h", dev); o.wthl = opt(out, "wthl", dev); o.wqt = opt(out, "wqt", dev);
-  o.Tv = opt(out, "Tv", dev); o.THL = opt(out, "THL", dev); o.QT = opt(out, "QT", dev); o.Zf = opt(out, "Zf", dev);
-  o.Zh = opt(out, "Zh", dev);
-  o.bracket = (int32_t*)opt(out, "bracket", dev);
-  o.slab_idx = (int32_t*)opt(out, "slab_idx", dev);
+  o.f_u = opt(out, "f_u", dev, st, ck); o.f_v = opt(out, "f_v", dev, st, ck); o.f_thl = opt(out, "f_thl", dev, st, ck);
+  o.f_qt = opt(out, "f_qt", dev, st, ck); o.f_ql = opt(out, "f_ql", dev, st, ck); o.ql_ref = opt(out, "ql_ref", dev, st, ck);
+  o.u = opt(out, "u", dev, st, ck); o.v = opt(out, "v", dev, st, ck); o.thl = opt(out, "thl", dev, st, ck);
+  o.qt = opt(out, "qt", dev, st, ck);
+  o.f_ps = opt(out, "f_ps", dev, st, nc); o.ps = opt(out, "ps", dev, st, nc);
+  o.z0m = opt(out, "z0m", dev, st, nc); o.z0h = opt(out, "z0h", dev, st, nc); o.wthl = opt(out, "wthl", dev, st, nc);
+  o.wqt = opt(out, "wqt", dev, st, nc);
+  o.Tv = opt(out, "Tv", dev, st, cl); o.THL = opt(out, "THL", dev, st, cl); o.QT = opt(out, "QT", dev, st, cl);
+  o.Zf = opt(out, "Zf", dev, st, cl);
+  o.Zh = opt(out, "Zh", dev, st, cl + nc);
+  o.bracket = (int32_t*)opt(out, "bracket", dev, at::kInt, ck);
+  o.slab_idx = (int32_t*)opt(out, "slab_idx", dev, at::kInt, cl);
+  TORCH_CHECK(!zh.has_value() || (zh->scalar_type() == at::kDouble && zh->numel() == nk), "zh must be float64 [nk]");
   check_rc(spc_gcm_to_les(handle_for(dev.index()), &g, (const double*)cptr(zf, dev, "zf"),
                           zh.has_value() ? (const double*)cptr(*zh, dev, "zh") : nullptr, (int)zf.numel(),
-                          les_prof.has_value() ? (const double*)cptr(*les_prof, dev, "les_prof") : nullptr,
-                          ps_les.has_value() ? cptr(*ps_les, dev, "ps_les") : nullptr, dt, factor, couple_surface ? 1 : 0,
+                          (const double*)opt_t(les_prof, "les_prof", dev, at::kDouble, 5 * ck),
+                          opt_t(ps_les, "ps_les", dev, st, nc), dt, factor, couple_surface ? 1 : 0,
                           &o, at::cuda::getCurrentCUDAStream(dev.index()).stream()),
            "spc_gcm_to_les");
 }
@@ -138,17 +160,28 @@ void les_to_gcm(const TDict& gcm, const at::Tensor& zf, const c10::optional<at::
   TORCH_CHECK(dev.is_cuda() && zf.scalar_type() == at::kDouble, "zf must be a float64 CUDA tensor");
   c10::cuda::CUDAGuard guard(dev);
   spc_gcm_cols g = gcm_struct(gcm, dev, false);
+  const at::ScalarType st = gcm.at("T").scalar_type();
+  const int64_t nk = zf.numel(), ck = (int64_t)g.ncol * nk, cl = (int64_t)g.ncol * g.nlev, nc = g.ncol;
+  TORCH_CHECK(layout == SPC_LAYOUT_KJI || layout == SPC_LAYOUT_IJK, "bad layout ", layout);
+  TORCH_CHECK(vol_dtype == SPC_F32 || vol_dtype == SPC_F64, "bad vol_dtype ", vol_dtype);
+  TORCH_CHECK(!zh.has_value() || (zh->scalar_type() == at::kDouble && zh->numel() == nk), "zh must be float64 [nk]");
   spc_les_prof l{};
-  l.prof = (const double*)req(les, "prof", dev, at::kDouble);
-  l.QL_ice = opt(les, "QL_ice", dev); l.T = opt(les, "T", dev); l.Rhobf = opt(les, "Rhobf", dev); l.A = opt(les, "A", dev);
-  l.mask = (const uint32_t*)opt(les, "mask", dev);
-  l.slab_idx = (const int32_t*)opt(les, "slab_idx", dev);
-  l.cnt = (const int32_t*)opt(les, "cnt", dev);
+  l.prof = (const double*)req(les, "prof", dev, at::kDouble, 5 * ck);
+  l.QL_ice = opt(les, "QL_ice", dev, st, ck); l.T = opt(les, "T", dev, st, ck); l.Rhobf = opt(les, "Rhobf", dev, st, ck);
+  l.A = opt(les, "A", dev, st, cl);
+  if (les.contains("mask")) {
+    TORCH_CHECK(nx > 0 && ny > 0, "mask given without nx, ny");
+    const int64_t mwords = nc * (int64_t)spc_mask_words_per_column((int)vol_dtype, (int)layout, (int)nx, (int)ny, (int)nk);
+    l.mask = (const uint32_t*)opt(les, "mask", dev, at::kInt, mwords);
+  }
+  l.slab_idx = (const int32_t*)opt(les, "slab_idx", dev, at::kInt, cl);
+  l.cnt = (const int32_t*)opt(les, "cnt", dev, at::kInt, ck);
   l.vol_dtype = (int)vol_dtype; l.layout = (int)layout; l.nx = (int)nx; l.ny = (int)ny;
   spc_gcm_tend o{};
-  o.tend = opt(out, "tend", dev); o.t = opt(out, "t", dev); o.A_d = opt(out, "A_d", dev);
-  o.cntslab = (int32_t*)opt(out, "cntslab", dev); o.bracket = (int32_t*)opt(out, "bracket", dev);
-  o.bracket_pf = (int32_t*)opt(out, "bracket_pf", dev); o.start_index = (int32_t*)opt(out, "start_index", dev);
+  o.tend = opt(out, "tend", dev, st, cl * SPC_NTEND); o.t = opt(out, "t", dev, st, ck); o.A_d = opt(out, "A_d", dev, st, cl);
+  o.cntslab = (int32_t*)opt(out, "cntslab", dev, at::kInt, cl); o.bracket = (int32_t*)opt(out, "bracket", dev, at::kInt, cl);
+  o.bracket_pf = (int32_t*)opt(out, "bracket_pf", dev, at::kInt, ck);
+  o.start_index = (int32_t*)opt(out, "start_index", dev, at::kInt, nc);
   check_rc(spc_les_to_gcm(handle_for(dev.index()), &g, (const double*)cptr(zf, dev, "zf"),
                           zh.has_value() ? (const double*)cptr(*zh, dev, "zh") : nullptr, (int)zf.numel(), &l, dt, factor,
                           conservative ? 1 : 0, &o, at::cuda::getCurrentCUDAStream(dev.index()).stream()),
@@ -159,7 +192,10 @@ void les_to_gcm(const TDict& gcm, const at::Tensor& zf, const c10::optional<at::
 
 TORCH_LIBRARY(spcpl_b200, m) {
   m.def("mask_words_per_column(int dtype, int layout, int nx, int ny, int nk) -> int", &mask_words_per_column);
-  m.def("slab_reduce(Tensor[] vols, int layout, float ql_thresh, Tensor prof, Tensor? cnt, Tensor? mask) -> ()", &slab_reduce);
+  // outputs are written in place: annotated where the schema language can say so; the `out` dictionaries of the two
+  // profile ops are mutated as well (Dict values cannot carry an alias annotation)
+  m.def("slab_reduce(Tensor[] vols, int layout, float ql_thresh, Tensor(a!) prof, Tensor(b!)? cnt, Tensor(c!)? mask) -> ()",
+        &slab_reduce);
   m.def("gcm_to_les(Dict(str, Tensor) gcm, Tensor zf, Tensor? zh, Tensor? les_prof, Tensor? ps_les, float dt, "
         "float factor, bool couple_surface, Dict(str, Tensor) out) -> ()", &gcm_to_les);
   m.def("les_to_gcm(Dict(str, Tensor) gcm, Tensor zf, Tensor? zh, Dict(str, Tensor) les, int nx, int ny, int layout, "

@@ -8,18 +8,30 @@ time step instead of the reference's two serial Python loops over LES models
     K2   gcm_to_les   forcings on the LES from the previous slab means        <- set_les_forcings
          [ the LES models time-step here; external to the coupling path ]
     K1   slab_reduce  slab means + cloud mask of the LES volumes              <- get_les_profiles
-    K3   les_to_gcm   tendencies on the GCM, packed [ncol][7][nlev]           <- set_gcm_tendencies
-    NCCL all_gather of the packed tendency block when columns are sharded
-    D2H  tendencies to the rank that owns the GCM
+    K3   les_to_gcm   cloud projection + tendencies, packed [ncol][7][nlev];  <- set_gcm_tendencies
+                      its epilogue also delivers the block: NVLink stores into the GCM owner's gather buffer
+                      (columns sharded over GPUs) or PCIe stores into the host GCM's pinned memory, and a
+                      completion flag - no separate collective, copy or host synchronisation
 
 Columns are independent, so ranks own contiguous column blocks and the only exchange is the
-tendency gather.
+tendency gather. The whole step - sharded or not - is three kernel launches with no
+host-side barrier, so it is recorded once into a CUDA graph (`capture()`).
+
+Level window. Tendencies of GCM levels above the LES top are zero (spcpl.py:494-533) and the
+forcings only need the GCM levels up to the first one above the LES top, so the step gives the same
+numbers when the GCM columns are cut off above that level: the kernels simply run on `nlw = nlev - lev0`
+levels. `set_levels()` re-views all profile buffers for a window; the host-facing steps use it so that
+only live levels cross PCIe (L91: 27 of 91 levels, L137: 38 of 137).
 """
+import os
+import time
+
 import numpy as np
 import torch
 
+from . import _abi
 from .constants import surf_vars
-from .coupler import GCM_FULL, GCM_HALF
+from .coupler import GCM_FULL, GCM_HALF, RemoteTargets
 
 
 def shard_columns(ncol_total, world_size, rank):
@@ -30,42 +42,88 @@ def shard_columns(ncol_total, world_size, rank):
 
 
 def gather_tendencies(tend_local, tend_all, group=None):
-    """The path's only exchange: all_gather of the packed [ncol_local][7][nlev]
-    tendency blocks into [ncol_local*world][7][nlev] so the rank that owns the GCM holds every
-    column's tendencies (reference analogue: 7 set_profile_tendency RPCs per column,
-    spcpl.py:535-542). NCCL on device tensors, gloo on CPU tensors (tests)."""
+    """The path's only exchange as a library collective: all_gather of the packed
+    [ncol_local][7][nlev] tendency blocks into [ncol_local*world][7][nlev] so the rank that owns the GCM holds every
+    column's tendencies (reference analogue: 7 set_profile_tendency RPCs per column, spcpl.py:535-542).
+    NCCL on device tensors, gloo on CPU tensors (tests). The default multi-GPU path does not call this: K3 stores
+    its block into the owner's buffer itself (CouplingPipeline, gather="p2p-owner")."""
     torch.distributed.all_gather_into_tensor(tend_all, tend_local, group=group)
     return tend_all
 
 
+def first_live_level(zgfull, zg_surface, zf_top, margin=1):
+    """Host-side bound of where tendencies can be non-zero: the smallest start_index over the given columns
+    (spcpl.py:494-498: GCM full levels strictly above the LES top get zero tendencies), computed from the HOST
+    profiles with the kernels' own float64 expression (Zgfull - Zghalf[-1]) / grav > zf[-1], minus `margin` levels
+    (one level above the LES top is needed as the upper bracket of the GCM->LES interpolation, spcpl.py:224-228).
+    zgfull [ncol][nlev], zg_surface [ncol] (= Zghalf[:, -1]); numpy arrays or CPU tensors."""
+    zgfull = torch.as_tensor(np.asarray(zgfull) if not isinstance(zgfull, torch.Tensor) else zgfull).double()
+    zs = torch.as_tensor(np.asarray(zg_surface) if not isinstance(zg_surface, torch.Tensor) else zg_surface).double()
+    zf = (zgfull - zs.reshape(-1, 1)) / 9.81
+    start = (zf > float(zf_top)).sum(dim=1)
+    return max(int(start.min()) - int(margin), 0)
+
+
+def window_columns(gcm, lev0):
+    """The GCM columns cut off above level lev0: profile arrays [:, lev0:], surface fields unchanged."""
+    if lev0 == 0:
+        return gcm
+    out = {}
+    for n, v in gcm.items():
+        out[n] = v[:, lev0:] if (n in GCM_FULL or n in GCM_HALF) else v
+    return out
+
+
 class GcmStaging(object):
     """Packed struct-of-arrays staging of the GCM inputs (gcm_vars + surf_vars, spcpl.py:32-33):
-    one pinned host buffer, one device buffer, one async copy per step."""
+    one pinned host buffer, one device buffer, one async copy per step. Sized for `nlev` levels;
+    `set_levels(nlw)` re-packs the views for a window of the lowest nlw levels (contiguous prefix of
+    both buffers, so the copy stays a single transfer of `nbytes` bytes)."""
 
     def __init__(self, ncol, nlev, dtype, device, pin=True):
-        self.ncol, self.nlev, self.dtype = ncol, nlev, dtype
-        sizes = [(n, (ncol, nlev)) for n in GCM_FULL] + [(n, (ncol, nlev + 1)) for n in GCM_HALF] + \
-                [(n, (ncol,)) for n in surf_vars]
-        total = sum(int(np.prod(s)) for _, s in sizes)
+        self.ncol, self.nlev_max, self.dtype = ncol, nlev, dtype
+        total = self.numel_for(ncol, nlev)
         self.host_buf = torch.empty(total, dtype=dtype, pin_memory=pin and torch.cuda.is_available())
         self.dev_buf = torch.empty(total, dtype=dtype, device=device)
-        self.host, self.dev = {}, {}
-        off = 0
-        for n, s in sizes:
+        self.esize = self.host_buf.element_size()
+        self.set_levels(nlev)
+
+    @staticmethod
+    def sizes(ncol, nlev):
+        return [(n, (ncol, nlev)) for n in GCM_FULL] + [(n, (ncol, nlev + 1)) for n in GCM_HALF] + \
+               [(n, (ncol,)) for n in surf_vars]
+
+    @classmethod
+    def numel_for(cls, ncol, nlev):
+        return sum(int(np.prod(s)) for _, s in cls.sizes(ncol, nlev))
+
+    @staticmethod
+    def views(buf, ncol, nlev):
+        out, off = {}, 0
+        for n, s in GcmStaging.sizes(ncol, nlev):
             cnt = int(np.prod(s))
-            self.host[n] = self.host_buf[off:off + cnt].view(*s)
-            self.dev[n] = self.dev_buf[off:off + cnt].view(*s)
+            out[n] = buf[off:off + cnt].view(*s)
             off += cnt
-        self.nbytes = total * self.host_buf.element_size()
+        return out
+
+    def set_levels(self, nlw):
+        if not 2 <= nlw <= self.nlev_max:
+            raise ValueError("level window %d outside [2, %d]" % (nlw, self.nlev_max))
+        self.nlev = nlw
+        self.numel = self.numel_for(self.ncol, nlw)
+        self.nbytes = self.numel * self.esize
+        self.host = self.views(self.host_buf, self.ncol, nlw)
+        self.dev = self.views(self.dev_buf, self.ncol, nlw)
 
     def fill_host(self, gcm):
-        """Copy a dict of numpy / CPU-tensor arrays into the pinned buffer (what the host GCM does)."""
+        """Copy a dict of numpy / CPU-tensor arrays (already cut to the current level window) into the pinned buffer
+        (what the host GCM does)."""
         for n, h in self.host.items():
             if n in gcm:
                 h.copy_(torch.as_tensor(np.ascontiguousarray(gcm[n])) if not isinstance(gcm[n], torch.Tensor) else gcm[n])
 
     def upload(self):
-        self.dev_buf.copy_(self.host_buf, non_blocking=True)
+        self.dev_buf[:self.numel].copy_(self.host_buf[:self.numel], non_blocking=True)
         return self.dev
 
 
@@ -113,7 +171,6 @@ def bind_host_thread_to_gpu(device):
     """Restricts this process to the CPUs NVML reports as local to `device` (its NUMA node), so that the pinned host
     pages it first touches and its PCIe copies stay on the GPU's side of the socket interconnect. Returns the CPU
     list, or None when NVML / the affinity call is unavailable (then nothing changes)."""
-    import os
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -130,38 +187,59 @@ def bind_host_thread_to_gpu(device):
         return None
 
 
+def _spin_until(read, value, timeout_s, what):
+    """Poll `read() >= value`: a short busy phase (the GPU step is tens of microseconds to milliseconds away), then
+    sleeps that back off to 0.2 ms so a long wait does not burn a core. x86-TSO / the C11 model of CPython's buffer
+    reads make a plain load sufficient for a word written with a release store by the GPU or by another process."""
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        if read() >= value:
+            return
+        n += 1
+        if n > 2000:
+            el = time.perf_counter() - t0
+            if el > timeout_s:
+                raise RuntimeError("%s: waited %.0f s" % (what, el))
+            time.sleep(min(2e-4, 1e-6 * (n - 2000)))
+
+
 class HostExchange(object):
     """Host side of a sharded step when the GCM lives in HOST memory of one process (OpenIFS does): one pinned
-    host buffer shared by all ranks of the node (a /dev/shm mapping that every rank registers with CUDA).
+    host buffer shared by all ranks of the node (a /dev/shm mapping that every rank maps for its GPU).
 
-        GCM owner   writes every rank's packed input block into `inp[r]`, then publishes the step number
-        every rank  waits for it, copies ITS block host->device, runs the step on its columns, copies ITS
-                    tendency block device->host into `out[r*ncol:(r+1)*ncol]`, publishes "done"
-        GCM owner   waits for all ranks: `out` holds [world*ncol][7][nlev], no device gather, no collective
+        GCM owner   writes every rank's packed input block (cut to the live level window) into `inp[r]`,
+                    then publishes (step number, lev0) in the header
+        every rank  waits for it, copies ITS block host->device (one copy over its own PCIe link) and replays the
+                    step; K3 stores ITS tendency block straight into the shared buffer's `out[r*ncol:(r+1)*ncol]` and
+                    then sets the rank's completion flag there (zero-copy PCIe stores from the kernel's epilogue)
+        GCM owner   polls the flags of all ranks: `out` holds [world*ncol][7][nlw] - no device gather, no collective,
+                    no device->host copy call and no stream synchronisation on the critical path
 
-    Every rank owns the same number of columns (as with GcmScatter); the constructor checks that collectively,
-    so the copies use every GPU's PCIe link at once instead of funnelling world*ncol columns through the
-    owner GPU's link (reference analogue: the master gathers every profile over its own channels,
-    spcpl.py:55-86, 535-542). Flags are int64 words in the same mapping (single writer each, monotonic).
-    Works on CPU tensors too (no registration) for the gloo tests."""
+    Every rank owns the same number of columns (checked collectively). Reference analogue: the master gathers every
+    profile over its own channels and sends every tendency back (spcpl.py:55-86, 535-542).
+    Memory ordering: header words are written by the owner process after the input blocks (x86-TSO keeps the order;
+    readers poll the step word first); GPU flags are release stores at system scope after a system-wide fence.
+    Works on CPU tensors too (no mapping; `host_step` is then driven by the gloo tests with a host-side stand-in)."""
 
-    FLAG_WORDS = 64
+    HEADER_WORDS = 8     # int64: [0] step number of the inputs, [1] lev0 of their level window
 
-    def __init__(self, staging, world, rank, owner=0, group=None, register=True, tag="x", timeout_s=60.0):
-        import os
-        self.staging, self.world, self.rank, self.owner, self.group = staging, world, rank, owner, group
-        self.timeout_s = timeout_s
-        ncol, nlev, dtype = staging.ncol, staging.nlev, staging.dtype
+    def __init__(self, pipe, world, rank, owner=0, group=None, register=True, tag="x", timeout_s=60.0, window=True):
+        self.pipe, self.world, self.rank, self.owner, self.group = pipe, world, rank, owner, group
+        self.timeout_s, self.window = timeout_s, window
+        staging = pipe.staging
+        ncol, nlev, dtype = staging.ncol, staging.nlev_max, staging.dtype
+        self.ncol, self.nlev = ncol, nlev
         esize = torch.empty((), dtype=dtype).element_size()
-        self.per_rank_in = staging.host_buf.numel()
-        self.per_rank_out = ncol * 7 * nlev
+        self.esize = esize
+        self.per_rank_in = GcmStaging.numel_for(ncol, nlev)
         nin = world * self.per_rank_in * esize
-        nout = world * self.per_rank_out * esize
+        nout = world * ncol * 7 * nlev * esize
         al = lambda n: (n + 4095) // 4096 * 4096
-        self._off_out = al(self.FLAG_WORDS * 8)
+        self._off_flags = al(self.HEADER_WORDS * 8)
+        self._off_out = self._off_flags + al(_abi.SYNC_WORDS * 4)
         self._off_in = self._off_out + al(nout)
         self.nbytes = self._off_in + al(nin)
-        path = "/dev/shm/spcpl_b200_%s_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "r"), tag)
         # every phase ends in an all_reduce(MIN) of "it worked here", so that all ranks either get the buffer or raise
         # together - a rank that fails alone must never leave the others waiting in a collective
         dev = "cuda" if torch.distributed.get_backend(group) == "nccl" else "cpu"
@@ -170,30 +248,35 @@ class HostExchange(object):
         if int(shape[0]) != -int(shape[1]) or int(shape[2]) != -int(shape[3]):
             raise ValueError("HostExchange needs the same number of columns and levels on every rank "
                              "(columns %d..%d, levels %d..%d)" % (int(shape[0]), -int(shape[1]), int(shape[2]), -int(shape[3])))
-        err = None
+        err, path = None, None
         try:
-            if rank == owner:
-                with open(path, "wb") as f:
-                    f.truncate(self.nbytes)
+            if rank == owner:       # private, unpredictable name; O_EXCL | O_NOFOLLOW semantics of mkstemp, mode 0600
+                import tempfile
+                fd, path = tempfile.mkstemp(prefix="spcpl_b200_%s_" % tag, dir="/dev/shm")
+                os.ftruncate(fd, self.nbytes)
+                os.close(fd)
         except Exception as e:          # noqa: BLE001
             err = e
         ok = self._agree(err is None, group)
-        self.raw, self.registered = None, False
+        names = [path]
+        if ok:
+            torch.distributed.broadcast_object_list(names, src=owner, group=group)
+            path = names[0]
+        self.raw, self.registered, self.dev_base = None, False, None
         if ok:
             try:
                 self.raw = torch.from_file(path, shared=True, size=self.nbytes, dtype=torch.uint8)
                 # first touch: this rank's input and output blocks are allocated on the NUMA node it runs on
                 self.raw[self._off_in + rank * self.per_rank_in * esize:self._off_in + (rank + 1) * self.per_rank_in * esize].zero_()
-                self.raw[self._off_out + rank * self.per_rank_out * esize:self._off_out + (rank + 1) * self.per_rank_out * esize].zero_()
-                if register and torch.cuda.is_available():
-                    rc = torch.cuda.cudart().cudaHostRegister(self.raw.data_ptr(), self.nbytes, 0)
-                    if int(rc) != 0:
-                        raise RuntimeError("cudaHostRegister failed (%s)" % (rc,))
+                o0 = self._off_out + rank * ncol * 7 * nlev * esize
+                self.raw[o0:o0 + ncol * 7 * nlev * esize].zero_()
+                if register and pipe.cpl is not None:
+                    self.dev_base = pipe.cpl.host_register(self.raw)
                     self.registered = True
             except Exception as e:      # noqa: BLE001
                 err = e
             ok = self._agree(err is None, group)
-        if rank == owner:
+        if rank == owner and path is not None:
             try:
                 os.unlink(path)        # the mapping stays alive in every process; nothing is left behind
             except OSError:
@@ -201,13 +284,20 @@ class HostExchange(object):
         if not ok:
             self.close()
             raise RuntimeError("HostExchange: shared pinned host buffer unavailable on at least one rank (%s)" % (err,))
-        self.flags = self.raw[:self.FLAG_WORDS * 8].view(torch.int64)          # [0] inputs ready, [1+r] rank r done
-        self.out = self.raw[self._off_out:self._off_out + nout].view(dtype).view(world * ncol, 7, nlev)
-        self.inp = self.raw[self._off_in:self._off_in + nin].view(dtype).view(world, self.per_rank_in)
+        self.header = self.raw[:self.HEADER_WORDS * 8].view(torch.int64)
+        self.flags = self.raw[self._off_flags:self._off_flags + _abi.SYNC_WORDS * 4].view(torch.int32)
+        self._out_flat = self.raw[self._off_out:self._off_out + nout].view(dtype)
+        self._in_flat = self.raw[self._off_in:self._off_in + nin].view(dtype)
+        self.inp = self._in_flat.view(world, self.per_rank_in)
         if rank == owner:
+            self.header.zero_()
             self.flags.zero_()
-        torch.distributed.barrier(group=group)
+        self._hdr_np, self._flags_np = self.header.numpy(), self.flags.numpy()    # plain loads for the polling loops
+        self.lev0 = 0
         self.step_no = 0
+        if self.registered:      # K3 of this rank stores into the shared buffer and signals its flag there
+            pipe.bind_host_output(self.dev_base + self._off_out, self.dev_base + self._off_flags, col0=rank * ncol, slot=rank)
+        torch.distributed.barrier(group=group)
 
     @staticmethod
     def _agree(ok, group):
@@ -218,123 +308,203 @@ class HostExchange(object):
 
     def close(self):
         if self.registered:
-            torch.cuda.cudart().cudaHostUnregister(self.raw.data_ptr())
+            torch.cuda.synchronize()
+            self.pipe.cpl.host_unregister(self.raw)
             self.registered = False
 
-    def fill_inputs(self, gcm_all):
-        """Owner only. gcm_all: dict of [world*ncol, ...] host arrays in global column order (what
-        gather_gcm_data fetched from the host GCM), packed per rank in GcmStaging order."""
-        st, ncol = self.staging, self.staging.ncol
-        for r in range(self.world):
-            off = 0
-            for n, h in st.host.items():
-                cnt = h.numel()
-                src = gcm_all[n][r * ncol:(r + 1) * ncol]
-                src = src if isinstance(src, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(src))
-                self.inp[r, off:off + cnt].view(h.shape).copy_(src)
-                off += cnt
+    def out(self, nlw=None):
+        """[world*ncol][7][nlw] view of the shared output region for the current (or given) level window."""
+        nlw = self.nlev - self.lev0 if nlw is None else nlw
+        return self._out_flat[:self.world * self.ncol * 7 * nlw].view(self.world * self.ncol, 7, nlw)
 
-    def _wait(self, word, value):
-        import time
-        t0 = time.perf_counter()
-        while int(self.flags[word]) < value:
-            if time.perf_counter() - t0 > self.timeout_s:
-                raise RuntimeError("HostExchange: rank %d waited %.0f s for flag %d >= %d" % (self.rank, self.timeout_s, word, value))
+    def fill_inputs(self, gcm_all, zf_top=None):
+        """Owner only. gcm_all: dict of [world*ncol, ...] host arrays (all nlev levels) in global column order - what
+        gather_gcm_data fetched from the host GCM. Chooses the level window of the step from the heights of ALL
+        columns and packs every rank's block, cut to the window, in GcmStaging order."""
+        ncol = self.ncol
+        lev0 = 0
+        if self.window:
+            top = self.pipe._zf_top if zf_top is None else zf_top
+            lev0 = first_live_level(gcm_all["Zgfull"], np.asarray(gcm_all["Zghalf"])[:, -1], top)
+        self._next_lev0 = lev0
+        nlw = self.nlev - lev0
+        per = GcmStaging.numel_for(ncol, nlw)
+        for r in range(self.world):
+            views = GcmStaging.views(self.inp[r, :per], ncol, nlw)
+            for n, h in views.items():
+                src = gcm_all[n][r * ncol:(r + 1) * ncol]
+                if n in GCM_FULL or n in GCM_HALF:
+                    src = src[:, lev0:]
+                src = src if isinstance(src, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(src))
+                h.copy_(src)
 
     def publish_inputs(self):
         """Owner: the input blocks of the next step are in place."""
         self.step_no += 1
-        self.flags[0] = self.step_no
+        self.header[1] = getattr(self, "_next_lev0", 0)
+        self.header[0] = self.step_no
 
-    def fetch_inputs(self, pipe):
-        """All ranks, once per step (the owner after fill_inputs): wait for the step's inputs and stage this rank's
-        block on its device. Returns the rank's device views (pipe.staging.dev)."""
+    def fetch_inputs(self):
+        """All ranks, once per step (the owner after fill_inputs): wait for the step's inputs, adopt their level
+        window and stage this rank's block on its device. Returns the rank's device views (pipe.staging.dev)."""
+        pipe = self.pipe
         if self.rank == self.owner:
             self.publish_inputs()
         else:
             self.step_no += 1
-        self._wait(0, self.step_no)
-        pipe.staging.dev_buf.copy_(self.inp[self.rank], non_blocking=True)
+        hdr = self._hdr_np
+        _spin_until(lambda: int(hdr[0]), self.step_no, self.timeout_s, "HostExchange rank %d: inputs of step %d" % (self.rank, self.step_no))
+        self.lev0 = int(hdr[1])
+        nlw = self.nlev - self.lev0
+        if pipe.nlw != nlw:
+            pipe.set_levels(nlw)
+        n = pipe.staging.numel
+        pipe.staging.dev_buf[:n].copy_(self.inp[self.rank, :n], non_blocking=True)
         return pipe.staging.dev
 
-    def put_tendencies(self, pipe):
-        """All ranks, once per step after K3: this rank's tendency block goes to its rows of the shared `out`; the
-        owner returns when every rank's block has landed (`out` is complete on the owner only)."""
-        lo = self.rank * pipe.ncol
-        self.out[lo:lo + pipe.ncol].copy_(pipe.tend, non_blocking=True)
-        if pipe.tend.is_cuda:
-            torch.cuda.current_stream(pipe.tend.device).synchronize()
-        self.flags[1 + self.rank] = self.step_no
+    def wait_tendencies(self):
+        """After the step has been launched. The owner returns when every rank's K3 has signalled that its block is in
+        the shared buffer (`out()` is complete on the owner only); the other ranks return at once. Without a mapped
+        buffer (CPU tests) every rank copies its block and sets its flag from the host."""
+        pipe = self.pipe
+        if not self.registered:
+            lo = self.rank * self.ncol
+            self.out()[lo:lo + self.ncol].copy_(pipe.tend)
+            pipe.epoch += 1
+            self.flags[_abi.SYNC_FLAG0 + self.rank] = pipe.epoch
         if self.rank == self.owner:
+            fl, want = self._flags_np, pipe.epoch
             for r in range(self.world):
-                self._wait(1 + r, self.step_no)
-        return self.out
+                _spin_until(lambda: int(fl[_abi.SYNC_FLAG0 + r]), want, self.timeout_s,
+                            "HostExchange: completion flag of rank %d (step %d)" % (r, self.step_no))
+        return self.out()
 
-    def step(self, pipe, dt=900.0, f_les=1.0, f_gcm=1.0):
+    def step(self, dt=900.0, f_les=1.0, f_gcm=1.0):
         """One sharded host-to-host step (all ranks call it; the owner refreshes the inputs with fill_inputs()
-        beforehand when the GCM has moved on). Returns (forcings, out) - `out` is complete on the owner only."""
-        self.fetch_inputs(pipe)
-        frc = pipe.step_device(dt, f_les, f_gcm)
-        return frc, self.put_tendencies(pipe)
+        beforehand when the GCM has moved on). Returns (forcings, out, lev0): `out` [world*ncol][7][nlev-lev0] is
+        complete on the owner only; tendencies of the levels above lev0 are zero."""
+        self.fetch_inputs()
+        frc = self.pipe.step(dt, f_les, f_gcm)
+        return frc, self.wait_tendencies(), self.lev0
 
 
 class CouplingPipeline(object):
-    """State + step of the GPU coupling path for this rank's columns."""
+    """State + step of the GPU coupling path for this rank's columns.
+
+    gather: how the packed tendency block reaches the rank that owns the GCM when columns are sharded
+      False / None   stays on this rank (single GPU, or the host exchange delivers it)
+      "p2p-owner"    K3 stores it into the owner's gather buffer over NVLink (all the path needs); default in bench.py
+      "p2p"          K3 stores it into every rank's gather buffer (an all-gather)
+      "nccl" / True  all_gather_into_tensor after K3 (the library collective; not graph-captured)
+    With a p2p mode the launch ends in K3's own device-side barrier (flags in symmetric memory), so the sharded step
+    needs no NCCL call and no host synchronisation."""
 
     def __init__(self, cpl, zf, zh, ncol, nlev, dtype=torch.float32, couple_surface=True, layout="kji",
-                 ql_thresh=0.0, group=None, gather=True):
+                 ql_thresh=0.0, group=None, gather=True, owner=0):
         self.cpl = cpl
         dev = cpl.device
         self.zf = torch.as_tensor(np.asarray(zf, dtype=np.float64)).to(dev)
         self.zh = torch.as_tensor(np.asarray(zh, dtype=np.float64)).to(dev)
         self.nk = int(self.zf.shape[0])
         self._zf_top = float(np.asarray(zf, dtype=np.float64)[-1])
-        self._tend_live = None
         self.ncol, self.nlev, self.dtype = ncol, nlev, dtype
         self.couple_surface, self.layout, self.ql_thresh = couple_surface, layout, ql_thresh
         self.staging = GcmStaging(ncol, nlev, dtype, dev)
-        self.gcm = self.staging.dev
         self.vols = None            # five LES volumes (device-resident LES state)
         self.aux = None             # LES-internal profiles: QL_ice, T, Rhobf, PS ...
         self.slab = None            # last K1 result
-        self.tend = torch.zeros((ncol, 7, nlev), dtype=dtype, device=dev)
         self.group = group
-        self.world = 1
-        self.rank = 0
+        self.world, self.rank, self.owner = 1, 0, owner
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(group)
             self.rank = torch.distributed.get_rank(group)
-        self.gather = gather and self.world > 1
-        # gather mode: True / "nccl" = all_gather_into_tensor after K3; "p2p" = fused gather, K3 stores
-        # its block straight into every rank's gather buffer over NVLink (symmetric memory) and a
-        # device-side barrier replaces the collective.
-        #   "p2p-owner": same, but only the GCM-owning rank (rank 0) receives the blocks - all the path needs.
-        self.gather_mode = gather if (self.gather and gather in ("p2p", "p2p-owner")) else "nccl"
-        self.symm = None
-        self.peer_ptrs = None
+        self.gather = bool(gather) and self.world > 1
+        self.gather_mode = (gather if gather in ("p2p", "p2p-owner") else "nccl") if self.gather else None
+        self._tend_buf = torch.zeros(ncol * 7 * nlev, dtype=dtype, device=dev)
+        self._host_buf = None       # pinned mirror of the (gathered) block, allocated on first use
+        self.remote = None          # RemoteTargets of K3 (peer gather buffers or pinned host memory)
+        self.epoch = 0              # host mirror of the sync epoch: K3 launches with the completion protocol so far
+        self._p2p = None
+        self._all_buf = None
+        self._host_flags = None
         if self.gather and self.gather_mode != "nccl":
             import torch.distributed._symmetric_memory as symm_mem
             grp = group if group is not None else torch.distributed.group.WORLD
-            # two gather buffers used alternately: while a rank still reads step n's buffer (D2H to the
-            # GCM), its peers may already store step n+1 into the other one; one barrier per step suffices
-            self._p2p = []
+            # two gather buffers used alternately (selected by the epoch inside K3): while a rank still reads step n's
+            # buffer (D2H to the GCM), its peers may already store step n+1 into the other one
+            bufs, sets = [], []
             for _ in range(2):
-                buf = symm_mem.empty((ncol * self.world, 7, nlev), dtype=dtype, device=dev)
+                buf = symm_mem.empty(ncol * self.world * 7 * nlev, dtype=dtype, device=dev)
                 buf.zero_()
                 hdl = symm_mem.rendezvous(buf, grp)
                 ptrs = [int(p) for p in hdl.buffer_ptrs]
-                if self.gather_mode == "p2p-owner":
-                    ptrs = [ptrs[0]]                      # rank 0 owns the GCM
-                self._p2p.append((buf, hdl, ptrs))
-            self._p2p_step = 0
-            self.tend_all, self.symm, self.peer_ptrs = self._p2p[0]
-        else:
-            self.tend_all = torch.zeros((ncol * self.world, 7, nlev), dtype=dtype, device=dev) if self.gather else self.tend
-        self.tend_host = torch.empty(self.tend_all.shape, dtype=dtype, pin_memory=True)
+                sets.append([ptrs[owner]] if self.gather_mode == "p2p-owner" else ptrs)
+                bufs.append((buf, hdl))
+            sync = symm_mem.empty(_abi.SYNC_WORDS, dtype=torch.int32, device=dev)
+            sync.zero_()
+            shdl = symm_mem.rendezvous(sync, grp)
+            self._p2p = (bufs, sync, shdl)
+            self.remote = RemoteTargets(sets, col0=self.rank * ncol, sync=sync, signal=[int(p) for p in shdl.buffer_ptrs],
+                                        slot=self.rank, n_wait=self.world)
+            torch.cuda.synchronize(dev)
+            torch.distributed.barrier(group=group)      # every sync block is zero before anyone's first K3
+        elif self.gather:
+            self._all_buf = torch.zeros(ncol * self.world * 7 * nlev, dtype=dtype, device=dev)
         self.k1_events = None       # optional [(start, end)] CUDA events around K1 (bench roofline)
-        self._graph = None          # CUDA graph of step_device (capture())
-        self._graph_frc = self._graph_args = None
-        self._graph_launches = 0
+        self._graphs = {}           # (nlw, dt, f_les, f_gcm) -> (graph, forcings, launches)
+        self._out_cache = {}        # nlw -> (K2 outputs, K3 outputs): written in place every step
+        self.set_levels(nlev)
+
+    # level window ------------------------------------------------------------------------------
+    def set_levels(self, nlw):
+        """Run the step on the lowest `nlw` GCM levels (module docstring, "Level window"). Re-views the staging
+        buffers, the packed tendency block and the gather / host targets; the buffers themselves stay."""
+        self.staging.set_levels(nlw)
+        self.nlw = nlw
+        self.gcm = self.staging.dev
+        n = self.ncol * 7 * nlw
+        self.tend = self._tend_buf[:n].view(self.ncol, 7, nlw)
+        return self
+
+    @property
+    def tend_all(self):
+        """The gathered block [ncol*world][7][nlw] of the LAST completed step (valid on the GCM owner; on every rank
+        with gather="p2p"/"nccl"); the local block when nothing is gathered."""
+        n = self.ncol * self.world * 7 * self.nlw
+        if self._p2p is not None:
+            buf = self._p2p[0][(self.epoch - 1) & 1][0] if self.epoch > 0 else self._p2p[0][0][0]
+            return buf[:n].view(self.ncol * self.world, 7, self.nlw)
+        if self._all_buf is not None:
+            return self._all_buf[:n].view(self.ncol * self.world, 7, self.nlw)
+        return self.tend
+
+    @property
+    def tend_host(self):
+        """Pinned host mirror of tend_all for the current level window."""
+        total = self.ncol * self.world * 7 * self.nlev
+        if self._host_buf is None:
+            self._host_buf = torch.zeros(total, dtype=self.dtype, pin_memory=True)
+        n = self.ncol * self.world * 7 * self.nlw
+        return self._host_buf[:n].view(self.ncol * self.world, 7, self.nlw)
+
+    def bind_host_output(self, out_ptr=None, flags_ptr=None, col0=0, slot=0):
+        """Make K3 deliver this rank's tendency block to HOST memory itself: zero-copy stores into a pinned buffer
+        [..][7][nlw] at column offset col0 and a completion flag next to it (RemoteTargets). Without arguments the
+        pipeline's own pinned mirror (`tend_host`) and a private flag block are used (single-GPU host step)."""
+        if self.gather:
+            raise RuntimeError("bind_host_output is for pipelines without a device gather (gather=False)")
+        if out_ptr is None:
+            self.tend_host                                  # allocate
+            self._host_flags = torch.zeros(_abi.SYNC_WORDS, dtype=torch.int32, pin_memory=True)
+            self._host_flags_np = self._host_flags.numpy()
+            out_ptr = self.cpl.host_device_pointer(self._host_buf)
+            flags_ptr = self.cpl.host_device_pointer(self._host_flags)
+        self._sync_dev = torch.zeros(_abi.SYNC_WORDS, dtype=torch.int32, device=self.cpl.device)
+        self.remote = RemoteTargets([[out_ptr]], col0=col0, sync=self._sync_dev, signal=[flags_ptr], slot=slot, n_wait=0)
+        self.epoch = 0
+        self._graphs.clear()
+        torch.cuda.synchronize(self.cpl.device)
+        return self
 
     # LES side --------------------------------------------------------------------------------
     def attach_les(self, vols, aux):
@@ -354,102 +524,114 @@ class CouplingPipeline(object):
         return self.slab
 
     # one coupled step -------------------------------------------------------------------------
+    def _outs(self):
+        return self._out_cache.setdefault(self.nlw, [None, None])
+
     def forcings(self, dt, factor):
         """K2 (set_les_forcings for all columns, spcpl.py:299-385)."""
         prof = self.slab["prof"] if self.slab is not None else None
-        return self.cpl.gcm_to_les(self.gcm, self.zf, self.zh, prof, self.aux["PS"] if prof is not None else None,
-                                   dt, factor, self.couple_surface)
+        outs = self._outs()
+        outs[0] = self.cpl.gcm_to_les(self.gcm, self.zf, self.zh, prof, self.aux["PS"] if prof is not None else None,
+                                      dt, factor, self.couple_surface, out=outs[0])
+        return outs[0]
 
     def tendencies(self, frc, dt, factor, conservative=False):
-        """K3 (set_gcm_tendencies for all columns, spcpl.py:388-555) + the tendency gather."""
-        if self.gather and self.gather_mode != "nccl":
-            self.tend_all, self.symm, self.peer_ptrs = self._p2p[self._p2p_step & 1]
-            self._p2p_step += 1
-            res = self.cpl.les_to_gcm(self.gcm, self.zf, self.zh, self.slab, self.aux, frc["slab_idx"], dt, factor,
-                                      conservative=conservative, tend_out=self.tend, peer_ptrs=self.peer_ptrs,
-                                      peer_col0=self.rank * self.ncol)
-            self.symm.barrier(channel=0)     # every rank's NVLink stores have landed everywhere
-            return res
-        res = self.cpl.les_to_gcm(self.gcm, self.zf, self.zh, self.slab, self.aux, frc["slab_idx"], dt, factor,
-                                  conservative=conservative, tend_out=self.tend)
-        if self.gather:
+        """K3 (set_gcm_tendencies for all columns, spcpl.py:388-555), which also delivers the block (class docstring)."""
+        outs = self._outs()
+        outs[1] = self.cpl.les_to_gcm(self.gcm, self.zf, self.zh, self.slab, self.aux, frc["slab_idx"], dt, factor,
+                                      conservative=conservative, tend_out=self.tend, remote=self.remote, out=outs[1])
+        if self.remote is not None and self.remote.sync is not None and not torch.cuda.is_current_stream_capturing():
+            self.epoch += 1
+        if self.gather and self.gather_mode == "nccl":
             gather_tendencies(self.tend, self.tend_all, self.group)
-        return res
+        return outs[1]
 
     def step_device(self, dt=900.0, f_les=1.0, f_gcm=1.0):
-        """K2 -> K1 -> K3 (+gather) with everything already resident in HBM."""
+        """K2 -> K1 -> K3 (incl. the tendency delivery) with everything already resident in HBM."""
         frc = self.forcings(dt, f_les)
         self.les_profiles()
         self.tendencies(frc, dt, f_gcm)
         return frc
 
+    def step(self, dt=900.0, f_les=1.0, f_gcm=1.0):
+        """The device step: replayed from its CUDA graph when one has been captured for the current level window
+        and factors, else launched eagerly."""
+        g = self._graphs.get((self.nlw, dt, f_les, f_gcm))
+        if g is None:
+            return self.step_device(dt, f_les, f_gcm)
+        graph, frc, launches = g
+        graph.replay()
+        self.cpl.launches += launches
+        if self.remote is not None and self.remote.sync is not None:
+            self.epoch += 1
+        return frc
+
     # CUDA graph of the device step ---------------------------------------------------------------
     def capture(self, dt=900.0, f_les=1.0, f_gcm=1.0, warmup=2):
-        """Records K2 -> K1 -> cloud projection -> K3 of a single-rank step once into a CUDA graph, so that a step is
-        one graph launch instead of four calls through the C ABI. Worth it for small column batches, where the
-        step is launch-bound; at thousands of columns the host is far ahead of K1 anyway. All buffers of the
-        step (forcings, slab means, mask, tendencies) become static: `step_graph()` returns the same tensors
-        every time. Sharded runs (tendency gather on) keep the eager path."""
-        if self.gather:
-            raise RuntimeError("capture() records the single-rank step; with a tendency gather (gather=%r) run it eagerly "
-                               "(capturing the collective hung in testing and the fused gather's barrier is not capturable)"
-                               % self.gather_mode)
+        """Records K2 -> K1 -> K3 once into a CUDA graph, so that a step is one graph launch instead of three calls
+        through the C ABI. Sharded steps are captured too: the gather and its barrier are inside K3. All ranks must
+        call it together (the warm-up steps run the device barrier). All buffers of the step are static: `step()`
+        returns the same forcing tensors every time. Only the NCCL gather mode keeps the eager path."""
+        if self.gather and self.gather_mode == "nccl":
+            raise RuntimeError("capture() needs the fused gather (gather='p2p' / 'p2p-owner'): the NCCL collective is "
+                               "not recorded into the step graph")
         if self.k1_events is not None:
             raise RuntimeError("K1 event timing must be off during capture")
         cur = torch.cuda.current_stream(self.cpl.device)
         side = torch.cuda.Stream(self.cpl.device)
         side.wait_stream(cur)
-        with torch.cuda.stream(side):          # warm-up off the capture: lazy kernel attributes, allocator pools
-            for _ in range(warmup):
+        with torch.cuda.stream(side):          # warm-up off the capture: output buffers exist, allocator pools are warm
+            for _ in range(max(warmup, 1)):
                 self.step_device(dt, f_les, f_gcm)
         cur.wait_stream(side)
         l0 = self.cpl.launches
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             frc = self.step_device(dt, f_les, f_gcm)
-        self._graph, self._graph_frc, self._graph_launches = graph, frc, self.cpl.launches - l0
-        self._graph_args = (dt, f_les, f_gcm)
+        self._graphs[(self.nlw, dt, f_les, f_gcm)] = (graph, frc, self.cpl.launches - l0)
+        self.cpl.launches = l0
         return graph
 
-    def step_graph(self):
+    def step_graph(self, dt=900.0, f_les=1.0, f_gcm=1.0):
         """Replays the captured step on the current stream; returns the (static) forcing tensors."""
-        self._graph.replay()
-        self.cpl.launches += self._graph_launches
-        return self._graph_frc
+        if (self.nlw, dt, f_les, f_gcm) not in self._graphs:
+            raise RuntimeError("no graph captured for this level window / factors")
+        return self.step(dt, f_les, f_gcm)
 
-    def first_live_level(self):
-        """Host-side bound of where tendencies can be non-zero: the smallest start_index over this rank's columns
-        (spcpl.py:494-498: GCM full levels strictly above the LES top get zero), computed from the staged HOST
-        profiles with the kernels' own float64 expression (Zgfull - Zghalf[-1]) / grav > zf[-1], minus one level of
-        margin. Levels [0, first_live) of every tendency are exactly zero and need not travel."""
-        h = self.staging.host
-        zf = (h["Zgfull"].double() - h["Zghalf"].double()[:, -1:]) / 9.81
-        start = (zf > float(self._zf_top)).sum(dim=1)
-        return max(int(start.min()) - 1, 0)
+    def sync_error(self):
+        """Non-zero when a K3 launch gave up waiting for a peer's completion flag (20 s); reads one device word."""
+        sync = self.remote.sync if self.remote is not None else None
+        return 0 if sync is None else int(sync[_abi.SYNC_ERROR].item())
 
-    def step_host(self, dt=900.0, f_les=1.0, f_gcm=1.0, owner=0, compact=False):
-        """The step as the host GCM sees it: GCM profiles in pinned host memory in, tendencies in
-        pinned host memory out on the rank that owns the GCM. Synchronises before returning.
-        compact=True (single rank): only the levels that can be non-zero come back - returns
-        (forcings, (tend[:, :, first:], first)) with the block contiguous in pinned memory; `first` comes from
-        first_live_level(), evaluated on the host while the GPU runs the step."""
+    # host-facing step --------------------------------------------------------------------------
+    def first_live_level(self, gcm_host=None):
+        """lev0 of the level window for the given host columns (default: the staged ones, full levels)."""
+        h = self.staging.host if gcm_host is None else gcm_host
+        return first_live_level(h["Zgfull"], torch.as_tensor(np.asarray(h["Zghalf"]))[:, -1], self._zf_top)
+
+    def stage_host(self, gcm_host, window=True):
+        """The host GCM's part of gather_gcm_data: pick the level window of these columns, pack them (cut to the
+        window) into the pinned staging buffer. Returns lev0. Not per step unless the GCM state changed."""
+        lev0 = self.first_live_level(gcm_host) if window else 0
+        nlw = self.nlev - lev0
+        if nlw != self.nlw:
+            self.set_levels(nlw)
+        self.staging.fill_host(window_columns(gcm_host, lev0))
+        self.lev0 = lev0
+        return lev0
+
+    def step_host(self, dt=900.0, f_les=1.0, f_gcm=1.0, owner=0):
+        """The step as the host GCM sees it: GCM profiles in pinned host memory in (one H2D copy of the staged level
+        window), tendencies in pinned host memory out on the rank that owns the GCM. Returns (forcings, tend_host)
+        with tend_host [ncol*world][7][nlw] for the current window (levels above it are zero).
+        After bind_host_output() K3 writes tend_host itself and the host only polls the completion flag; otherwise the
+        (gathered) device block is copied back and the stream synchronised."""
         self.staging.upload()
-        if self._graph is not None and self._graph_args == (dt, f_les, f_gcm):
-            frc = self.step_graph()
-        else:
-            frc = self.step_device(dt, f_les, f_gcm)
-        if compact and not self.gather:
-            first = self.first_live_level()
-            nl = self.nlev - first
-            if self._tend_live is None:
-                self._tend_live = torch.empty(self.tend.numel(), dtype=self.dtype, device=self.cpl.device)
-            n = self.ncol * 7 * nl
-            dev = self._tend_live[:n].view(self.ncol, 7, nl)
-            dev.copy_(self.tend[:, :, first:])                      # strided -> contiguous, on the device
-            host = self.tend_host.view(-1)[:n].view(self.ncol, 7, nl)
-            host.copy_(dev, non_blocking=True)
-            torch.cuda.current_stream(self.cpl.device).synchronize()
-            return frc, (host, first)
+        frc = self.step(dt, f_les, f_gcm)
+        if self._host_flags is not None:
+            fl, want = self._host_flags_np, self.epoch
+            _spin_until(lambda: int(fl[_abi.SYNC_FLAG0]), want, 60.0, "step_host: K3 completion flag")
+            return frc, self.tend_host
         if self.rank == owner:
             self.tend_host.copy_(self.tend_all, non_blocking=True)
         torch.cuda.current_stream(self.cpl.device).synchronize()

@@ -123,13 +123,13 @@ def gather_gcm_data_sharded(gcm, batch, couple_surface=True):
         # the GCM's host memory is one pinned buffer shared by all ranks: every rank stages its own columns over
         # its own PCIe link (pipeline.HostExchange); the tendencies go back the same way (set_gcm_tendencies_all)
         if getattr(batch, "_exchange", None) is None:
-            batch._exchange = HostExchange(pipe.staging, pipe.world, pipe.rank, owner=0, group=pipe.group, tag="splib")
+            batch._exchange = HostExchange(pipe, pipe.world, pipe.rank, owner=0, group=pipe.group, tag="splib")
         if pipe.rank == 0:
             cols = batch.all_grid_indices
             data = {v: gcm.get_profile_fields(v, cols) for v in gcm_vars}
             data.update({v: gcm.get_surface_field(v, cols) for v in surf_vars})
-            batch._exchange.fill_inputs(data)
-        dev = batch._exchange.fetch_inputs(pipe)
+            batch._exchange.fill_inputs(data)       # cut to the live level window (pipeline.py, "Level window")
+        dev = batch._exchange.fetch_inputs()
         for i, les in enumerate(batch.models):
             for v in gcm_vars:
                 setattr(les, v, dev[v][i])
@@ -207,6 +207,7 @@ def set_les_state(les, u, v, thl, qt, ps=None):
         cpl.set_les_state(p.reshape(1, -1).double().contiguous(), synth.NOISE_AMP[f], synth.STREAM[f], b.nx, b.ny,
                           seed=b.seed, col0=b.col0 + les.i, dtype=b.dtype,
                           out=b.vols[LES_FIELDS.index(f)][les.i:les.i + 1])
+    b.state_version += 1
     if ps is not None:
         les.set_surface_pressure(ps)
 
@@ -332,10 +333,13 @@ def write_les_profiles(les):
 
 
 # --------------------------------------------------------------------------------- batched route
-def set_les_forcings_all(batch, dt_gcm, factor, couple_surface=True, firststep=False):
+def set_les_forcings_all(batch, dt_gcm, factor, couple_surface=True, firststep=False, qt_forcing='sp',
+                         variability_nudge_constant_T=False):
     """set_les_forcings for every LES of the batch in one K2 launch (first step: K1 first to get
     the slab means, spcpl.py:302-308). Forcings are written straight into the batch's tendency
-    buffers (what the per-LES set_tendency_* calls do one by one)."""
+    buffers (what the per-LES set_tendency_* calls do one by one). With qt_forcing == 'variance' the
+    qt-variability nudge follows for all columns in one launch once the LES clocks have left 0, exactly
+    where the reference runs it per LES (spcpl.py:377-382)."""
     pipe = batch.pipe
     if firststep or pipe.slab is None:
         pipe.les_profiles()
@@ -346,6 +350,12 @@ def set_les_forcings_all(batch, dt_gcm, factor, couple_surface=True, firststep=F
     if couple_surface:
         batch.surf.update(z0m=frc["z0m"], z0h=frc["z0h"], wt=frc["wthl"], wq=frc["wqt"])
     batch.last_forcings = frc
+    if qt_forcing == 'variance':                                                          # spcpl.py:377-382
+        if batch.model_time > 0:
+            from .nudge import variability_nudge_all
+            batch.last_nudge = variability_nudge_all(batch, dt_gcm, variability_nudge_constant_T)
+    elif qt_forcing != 'sp':
+        raise ValueError("qt_forcing must be 'sp' or 'variance', got %r" % (qt_forcing,))
     return frc
 
 
@@ -355,14 +365,15 @@ def get_les_profiles_all(batch):
 
 
 def set_gcm_tendencies_all(gcm, batch, dt_gcm, factor=1, conservative=False, to_host=True):
-    """set_gcm_tendencies for every LES in one K3 launch (+ NCCL all_gather when sharded); the
-    packed [ncol][7][nlev] block goes back to the host GCM in one copy."""
+    """set_gcm_tendencies for every LES in one K3 launch, which also gathers the packed [ncol][7][nlev] blocks on the
+    GCM-owning rank when the columns are sharded (NVLink stores, or PCIe stores into the host GCM's memory with
+    gather "host"; an NCCL all_gather with gather "nccl"); the block goes back to the host GCM in one copy."""
     pipe = batch.pipe
     res = pipe.tendencies(batch.last_forcings, float(dt_gcm), float(factor), conservative=conservative)
     if getattr(batch, "_exchange", None) is not None:          # sharded, host-resident GCM: no device gather
-        out = batch._exchange.put_tendencies(pipe)
+        out = batch._exchange.wait_tendencies()                # K3 stored every rank's block into the shared host buffer
         if to_host and gcm is not None and pipe.rank == 0:
-            gcm.set_profile_tendencies(batch.all_grid_indices, out)
+            gcm.set_profile_tendencies(batch.all_grid_indices, out, lev0=batch._exchange.lev0)
         return res
     if to_host and gcm is not None and pipe.rank == 0:
         pipe.tend_host.copy_(pipe.tend_all, non_blocking=True)

@@ -123,13 +123,16 @@ class gpu_gcm(dummy_base):
         v = vals.detach().cpu().numpy() if isinstance(vals, torch.Tensor) else np.asarray(vals)
         self.tendencies.setdefault(field, {})[int(index)] = v
 
-    def set_profile_tendencies(self, index, packed):
-        """Batched form: packed [ncol][7][nlev] host tensor in spc tendency order."""
+    def set_profile_tendencies(self, index, packed, lev0=0):
+        """Batched form: packed [ncol][7][nlev - lev0] host tensor in spc tendency order; with a level window
+        (lev0 > 0) the block holds the lowest levels only and the tendencies above are zero (spcpl.py:527-533)."""
         from .constants import TENDENCIES
         arr = packed.numpy() if isinstance(packed, torch.Tensor) else np.asarray(packed)
         idx = np.asarray(index, dtype=np.int64)
         for n, name in enumerate(TENDENCIES):
-            self.tendencies.setdefault(name[2:], {})["batch"] = (idx, arr[:, n, :].copy())
+            full = np.zeros((arr.shape[0], self.ktot), dtype=arr.dtype)
+            full[:, lev0:] = arr[:, n, :]
+            self.tendencies.setdefault(name[2:], {})["batch"] = (idx, full)
 
     def evolve_model_until_cloud_scheme(self):
         return True
@@ -180,6 +183,7 @@ class gpu_les_batch(object):
         self.ql_ref = z(ncol, nk)
         self.surf = {n: z(ncol) for n in ("z0m", "z0h", "wt", "wq")}
         self.model_time = 0.0
+        self.state_version = 0      # bumped whenever the 3-D state changes; keys the per-column slab cache
         self.models = [gpu_les(self, i) for i in range(ncol)]
 
     def initialize_state(self, profiles):
@@ -189,6 +193,7 @@ class gpu_les_batch(object):
             self.cpl.set_les_state(profiles[key].double().contiguous(), amp[f], synth.STREAM[f], self.nx, self.ny,
                                    seed=self.seed, col0=self.col0, dtype=self.dtype, out=self.vols[LES_FIELDS.index(f)])
         self._diagnose_ql(profiles["qt"].double())
+        self.state_version += 1
 
     def _diagnose_ql(self, qt_prof):
         """Stand-in saturation adjustment: ql = max(qt - qsat, 0) with qsat = <qt> + amp*s(k)."""
@@ -208,6 +213,7 @@ class gpu_les_batch(object):
         qt = self.vols[LES_FIELDS.index("QT")]
         torch.clamp(qt - self.qsat.to(self.dtype)[:, :, None, None], min=0, out=self.vols[LES_FIELDS.index("QL")])
         self.model_time = float(t_end)
+        self.state_version += 1
 
 
 class gpu_les(dummy_base):
@@ -244,7 +250,16 @@ class gpu_les(dummy_base):
         return [v[self.i:self.i + 1] for v in self.batch.vols]
 
     def _slab(self, want_mask=False):
-        return self.batch.cpl.slab_reduce(self.volumes(), want_cnt=want_mask, want_mask=want_mask)
+        """Slab means (+ counts and cloud mask) of this column. The five get_profile_* calls of one step
+        (spcpl.py:303-307) and get_cloudfraction share ONE reduction: the result is cached until the 3-D state
+        changes (batch.state_version), instead of re-reading all five volumes per call."""
+        key = (self.batch.state_version, bool(want_mask))
+        c = getattr(self, "_slab_cache", None)
+        if c is not None and c[0][0] == key[0] and (c[0][1] or not want_mask):
+            return c[1]
+        res = self.batch.cpl.slab_reduce(self.volumes(), want_cnt=want_mask, want_mask=want_mask)
+        self._slab_cache = (key, res)
+        return res
 
     def get_profile(self, name, return_request=False):
         f = LES_FIELDS.index(name)
@@ -308,6 +323,7 @@ class gpu_les(dummy_base):
         """values: (itot, jtot, ktot) array as in spcpl.set_les_state (spcpl.py:288-291)."""
         v = torch.as_tensor(values, dtype=self.batch.dtype, device=self.batch.cpl.device)
         self.batch.vols[LES_FIELDS.index(fid)][self.i].copy_(v.permute(2, 1, 0))
+        self.batch.state_version += 1
 
     def set_surface_pressure(self, value):
         self.batch.aux["PS"][self.i] = float(value)

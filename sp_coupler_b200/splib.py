@@ -174,7 +174,8 @@ def step():
                                    write=write_diagnostics,
                                    variability_nudge_constant_T=variability_nudge_constant_T)
     else:
-        spcpl.set_les_forcings_all(les_batch, delta_t, les_forcing_factor, cplsurf, firststep)
+        spcpl.set_les_forcings_all(les_batch, delta_t, les_forcing_factor, cplsurf, firststep, qt_forcing=qt_forcing,
+                                   variability_nudge_constant_T=variability_nudge_constant_T)
     torch.cuda.synchronize()
     forc += time.time()
 
@@ -222,7 +223,8 @@ def step_spinup(spinup_length):
                                    factor=les_spinup_forcing_factor, couple_surface=cplsurf, qt_forcing=qt_forcing,
                                    write=write_diagnostics)
     else:
-        spcpl.set_les_forcings_all(les_batch, spinup_length, les_spinup_forcing_factor, cplsurf, firststep)
+        spcpl.set_les_forcings_all(les_batch, spinup_length, les_spinup_forcing_factor, cplsurf, firststep,
+                                   qt_forcing=qt_forcing)                        # splib.py:375-382 (constant_T stays False)
     torch.cuda.synchronize()
     forc += time.time()
     les_wall_times, profiles = step_les_models(t_les + spinup_length, offset=0)   # splib.py:386

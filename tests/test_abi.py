@@ -27,7 +27,29 @@ def test_library_builds_and_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "missing export %s" % s
     assert sorted(_abi.SYMBOLS) == syms           # the ctypes binding covers the whole header
-    assert _abi.lib().spc_abi_version() == 1
+    assert _abi.lib().spc_abi_version() == 2
+
+
+def exported_symbols(path):
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    return sorted({l.split()[-1] for l in out.splitlines() if l.split() and l.split()[-1].startswith("spc_")})
+
+
+def test_production_library_exports_exactly_the_header():
+    """The converse of the test above: nothing named spc_* is exported that the header does not declare (the tuning
+    setters live in libspcpl_b200_tune.so only), the production library carries no sweep variants (size bound) and no
+    mutable process-global tuning state."""
+    import shutil
+    from sp_coupler_b200 import build
+    if shutil.which("nm") is None:
+        pytest.skip("nm not on PATH")
+    path = build.build()
+    assert exported_symbols(path) == header_symbols()
+    assert os.path.getsize(path) < 3 * 1024 * 1024
+    import subprocess
+    syms = subprocess.run(["nm", "-C", path], capture_output=True, text=True, check=True).stdout
+    assert "g_k1_variant" not in syms and "g_ijk_variant" not in syms and "g_k2_threads" not in syms
 
 
 def test_sass_is_sm100a_with_tma_bulk():

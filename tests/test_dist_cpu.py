@@ -5,6 +5,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -95,13 +96,23 @@ def test_gcm_scatter_delivers_each_ranks_columns(tmp_path):
 
 
 class _OraclePipe(object):
-    """Stand-in for CouplingPipeline on CPU tensors: step_device() = the oracle on this rank's staged columns."""
+    """Stand-in for CouplingPipeline on CPU tensors (what HostExchange touches): step() = the oracle on this rank's
+    staged columns, for whatever level window the exchange announced."""
+
+    cpl = None
+    _zf_top = float(synth.les_grid(NK, 200.0)[0][-1])
 
     def __init__(self, staging, col0):
         self.staging, self.ncol, self.col0 = staging, staging.ncol, col0
-        self.tend = torch.zeros((staging.ncol, 7, NLEV), dtype=torch.float64)
+        self.epoch = 0
+        self.set_levels(NLEV)
 
-    def step_device(self, dt, f_les, f_gcm):
+    def set_levels(self, nlw):
+        self.staging.set_levels(nlw)
+        self.nlw = nlw
+        self.tend = torch.zeros((self.ncol, 7, nlw), dtype=torch.float64)
+
+    def step(self, dt, f_les, f_gcm):
         zf, zh = synth.les_grid(NK, 200.0)
         gcm = {k: v.numpy() for k, v in self.staging.dev.items()}
         aux = synth.make_les_aux(self.ncol, NK, seed=5, col0=self.col0, ncol_total=NCOL)
@@ -112,15 +123,15 @@ class _OraclePipe(object):
         return r["forcings"]
 
 
-def _exchange_worker(rank, world, port, outdir):
+def _exchange_worker(rank, world, port, outdir, window):
     from sp_coupler_b200.pipeline import GcmStaging, HostExchange
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ncol = NCOL // world
     st = GcmStaging(ncol, NLEV, torch.float64, "cpu", pin=False)
-    ex = HostExchange(st, world, rank, owner=0, register=False, tag="cputest", timeout_s=120.0)
     pipe = _OraclePipe(st, rank * ncol)
+    ex = HostExchange(pipe, world, rank, owner=0, register=False, tag="cputest", timeout_s=120.0, window=window)
     full = synth.make_gcm_columns(NCOL, NLEV, seed=5)
     for it in range(2):
         if rank == 0:
@@ -128,21 +139,25 @@ def _exchange_worker(rank, world, port, outdir):
             if it == 1:
                 g["T"] = full["T"] + 1.5          # the host GCM moved on: every rank must see the new profiles
             ex.fill_inputs(g)
-        _, out = ex.step(pipe, 900.0, 1.0, 1.0)
+        _, out, lev0 = ex.step(900.0, 1.0, 1.0)
         if rank == 0:
             np.save(os.path.join(outdir, "out%d.npy" % it), out.numpy().copy())
+            np.save(os.path.join(outdir, "lev%d.npy" % it), np.array(lev0))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_host_exchange_shared_buffer(tmp_path):
+@pytest.mark.parametrize("window", [False, True])
+def test_host_exchange_shared_buffer(tmp_path, window):
     """Sharded host-to-host step: the GCM owner publishes every rank's inputs in one shared host buffer, each rank
-    stages its own block, computes, and writes its own tendency block back; the owner ends up with all columns."""
+    stages its own block, computes, and its tendency block lands in the shared buffer; the owner ends up with all
+    columns. With the level window only the GCM levels up to the first one above the LES top travel either way; the
+    block equals the full-level answer from lev0 on and everything above is zero."""
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_exchange_worker, args=(2, port, str(tmp_path), window), nprocs=2, join=True)
     zf, zh = synth.les_grid(NK, 200.0)
     full = synth.make_gcm_columns(NCOL, NLEV, seed=5)
     aux = synth.make_les_aux(NCOL, NK, seed=5)
@@ -153,7 +168,11 @@ def test_host_exchange_shared_buffer(tmp_path):
             g["T"] = full["T"] + 1.5
         r = nb.coupling_step(g, zf, zh, vols, aux, aux["PS"], 900.0, 1.0, 1.0, True)
         want = np.stack([r["tendencies"][k] for k in TENDENCIES], axis=1)
-        assert np.array_equal(np.load(str(tmp_path / ("out%d.npy" % it))), want), it
+        lev0 = int(np.load(str(tmp_path / ("lev%d.npy" % it))))
+        assert (lev0 > 0) == window
+        assert lev0 == max(int(r["tendencies"]["start_index"].min()) - 1, 0) or not window
+        assert np.array_equal(np.load(str(tmp_path / ("out%d.npy" % it))), want[:, :, lev0:]), it
+        assert not want[:, :, :lev0].any()
 
 
 def _unequal_worker(rank, world, port, outdir):
@@ -163,7 +182,7 @@ def _unequal_worker(rank, world, port, outdir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     st = GcmStaging(3 + rank, NLEV, torch.float64, "cpu", pin=False)      # 3 columns on rank 0, 4 on rank 1
     try:
-        HostExchange(st, world, rank, owner=0, register=False, tag="uneq")
+        HostExchange(_OraclePipe(st, 0), world, rank, owner=0, register=False, tag="uneq")
         msg = "no error"
     except ValueError as e:
         msg = str(e)

@@ -1,0 +1,148 @@
+"""Multi-GPU parity where the driver sees it (-m gpu): the sharded step on 2 / 4 / 8 GPUs of the box (one process per
+GPU, NCCL process group) must give, bit for bit, the tendencies one GPU computes for all columns - through every
+delivery route of the packed block (reference analogue: the 7 gcm.set_profile_tendency calls per column,
+/root/reference/splib/spcpl.py:535-542):
+
+  p2p-owner  K3 stores the block into the GCM owner's gather buffer over NVLink, in-kernel barrier   (eager + CUDA graph)
+  p2p        K3 stores it into every rank's buffer                                                    (eager + CUDA graph)
+  nccl       all_gather_into_tensor after K3
+  host       HostExchange: K3 stores it into the host GCM's pinned buffer shared by all ranks, level window, flag polling
+
+Skipped when the box has fewer GPUs than ranks (the 1-GPU round-end run); run it with `gpurun --gpus 2|8`.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+NCOL, NX, NK, NLEV, STEPS = 6, 16, 160, 91, 4
+
+
+def _worker(rank, world, port, outdir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    msgs = []
+    try:
+        from sp_coupler_b200 import synth
+        from sp_coupler_b200.coupler import Coupler
+        from sp_coupler_b200.pipeline import CouplingPipeline, HostExchange
+        cpl = Coupler(dev)
+        ntot = NCOL * world
+        zf, zh = synth.les_grid(NK)
+        up = lambda d: {k: torch.from_numpy(v).to(dev) for k, v in d.items()}
+
+        def inputs(col0, ncol):
+            gcm = synth.make_gcm_columns(ncol, NLEV, seed=11, dtype=np.float32, col0=col0, ncol_total=ntot)
+            aux = up(synth.make_les_aux(ncol, NK, seed=11, dtype=np.float32, col0=col0, ncol_total=ntot))
+            vols = synth.device_les_volumes(cpl, gcm, zf, NX, NX, seed=11, col0=col0)
+            return gcm, aux, vols
+
+        def run(pipe, vols, aux, gcm, graph, sync_each=True):
+            """STEPS steps; the LES state changes between steps so that a stale gather buffer would show. Without
+            sync_each the steps are queued back to back (ranks may run a step ahead of each other: the alternating
+            gather buffers and the in-kernel barrier must keep them apart) and only the last block is returned."""
+            vols = [v.clone() for v in vols]
+            pipe.staging.fill_host(gcm)
+            pipe.staging.upload()
+            pipe.attach_les(vols, aux)
+            pipe.les_profiles()
+            if graph:
+                pipe.capture(900.0, 1.0, 1.0)
+            outs = []
+            for it in range(STEPS):
+                vols[1].mul_(1.0 + 1e-3 * (it + 1))
+                vols[2].mul_(1.0 + 1e-2 * (it + 1))
+                pipe.step(900.0, 1.0, 1.0)
+                if sync_each or it == STEPS - 1:
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    outs.append(pipe.tend_all.clone())
+            return outs
+
+        # one GPU, all columns: what every sharded route must reproduce
+        gcm_all, aux_all, vols_all = inputs(0, ntot)
+        ref = run(CouplingPipeline(cpl, zf, zh, ntot, NLEV, torch.float32, gather=False), vols_all, aux_all, gcm_all, False)
+        assert not torch.equal(ref[0], ref[-1])
+        gcm, aux, vols = inputs(rank * NCOL, NCOL)
+        for mode, graph, sync_each in (("p2p-owner", False, True), ("p2p-owner", True, True), ("p2p-owner", False, False),
+                                       ("p2p-owner", True, False), ("p2p", False, True), ("p2p", True, False),
+                                       ("nccl", False, True)):
+            pipe = CouplingPipeline(cpl, zf, zh, NCOL, NLEV, torch.float32, gather=mode)
+            outs = run(pipe, vols, aux, gcm, graph, sync_each)
+            want = ref if sync_each else ref[-1:]
+            if rank == 0 or mode != "p2p-owner":
+                for it, (a, b) in enumerate(zip(outs, want)):
+                    if not torch.equal(a, b):
+                        msgs.append("%s graph=%s sync_each=%s step %d: gathered block differs from the single-GPU result"
+                                    % (mode, graph, sync_each, it))
+            if pipe.sync_error():
+                msgs.append("%s graph=%s: sync error %d" % (mode, graph, pipe.sync_error()))
+            del pipe
+        # host-resident GCM: shared pinned buffer, K3 stores into it
+        for graph in (False, True):
+            hp = CouplingPipeline(cpl, zf, zh, NCOL, NLEV, torch.float32, gather=False)
+            ex = HostExchange(hp, world, rank, owner=0, tag="disttest")
+
+            def host_step():
+                if rank == 0:
+                    ex.fill_inputs(gcm_all)
+                _, out, lev0 = ex.step(900.0, 1.0, 1.0)
+                dist.barrier()
+                return (out.clone(), lev0)
+
+            hv = [v.clone() for v in vols]
+            hp.attach_les(hv, aux)
+            hp.les_profiles()
+            if graph:       # adopt the window first, then record
+                if rank == 0:
+                    ex.fill_inputs(gcm_all)
+                ex.step(900.0, 1.0, 1.0)
+                hp.capture(900.0, 1.0, 1.0)
+            for it in range(STEPS):
+                hv[1].mul_(1.0 + 1e-3 * (it + 1))
+                hv[2].mul_(1.0 + 1e-2 * (it + 1))
+                out, lev0 = host_step()
+                if rank == 0:
+                    if lev0 <= 0:
+                        msgs.append("host graph=%s: no level window (lev0=%d)" % (graph, lev0))
+                    if not torch.equal(out, ref[it][:, :, lev0:].cpu()):
+                        msgs.append("host graph=%s step %d: host block differs from the single-GPU result" % (graph, it))
+                    if ref[it][:, :, :lev0].any():
+                        msgs.append("host graph=%s step %d: non-zero tendency above the window" % (graph, it))
+            if hp.sync_error():
+                msgs.append("host graph=%s: sync error %d" % (graph, hp.sync_error()))
+            torch.cuda.synchronize()
+            dist.barrier()
+            ex.close()
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        msgs.append("rank %d raised: %s\n%s" % (rank, e, traceback.format_exc()))
+    open(os.path.join(outdir, "rank%d.txt" % rank), "w").write("\n".join(msgs) if msgs else "ok")
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:           # noqa: BLE001
+        pass
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_step_equals_single_gpu(tmp_path, world):
+    import torch
+    import torch.multiprocessing as mp
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs on the box (has %d)" % (world, torch.cuda.device_count() if torch.cuda.is_available() else 0))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        assert open(str(tmp_path / ("rank%d.txt" % rank))).read() == "ok", rank

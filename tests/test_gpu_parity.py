@@ -115,7 +115,6 @@ def test_ijk_tma_path_matches_oracle(cpl, cuda_device, dtype, shape):
     5 x 32 vectors, nk % 32 == 0 for the mask): means, counts, per-point mask -> projected cloud cover, and the
     same bits from the CTA-per-item kernel it replaces."""
     import torch
-    from sp_coupler_b200 import _abi
     ncol, nx, ny, nk, nlev = shape
     case = cases.host_case(ncol, nx, ny, nk, nlev, dtype, layout=1, dz=25.0)
     ref = cases.oracle_step(case)
@@ -124,11 +123,15 @@ def test_ijk_tma_path_matches_oracle(cpl, cuda_device, dtype, shape):
     check_step(case, ref, slab, frc, tnd, RTOL[dtype])
     A, cs = cpl.cloud_fraction(slab, frc["slab_idx"])
     assert np.array_equal(n(cs), ref["cntslab"])
-    try:
-        _abi.lib().spc_tune_k1(101)            # force the older CTA-per-item kernel
-        old = cpl.slab_reduce(d["vols"], layout="ijk", want_mask=True)
-    finally:
-        _abi.lib().spc_tune_k1(100)
+    # the CTA-per-item kernel serves whatever the TMA plan rejects, e.g. volumes that are not 16-byte aligned:
+    # the same data one element into a larger buffer takes it
+    shifted = []
+    for v in d["vols"]:
+        flat = torch.empty(v.numel() + 1, dtype=v.dtype, device=v.device)
+        flat[1:].copy_(v.reshape(-1))
+        shifted.append(flat[1:].view(v.shape))
+    assert all(t.data_ptr() % 16 != 0 for t in shifted)
+    old = cpl.slab_reduce(shifted, layout="ijk", want_mask=True)
     assert torch.equal(old["cnt"], slab["cnt"]) and torch.equal(old["mask"], slab["mask"])
     assert relerr(n(old["prof"]), n(slab["prof"])) <= 1e-14
     again = cpl.slab_reduce(d["vols"], layout="ijk", want_mask=True)
@@ -375,8 +378,8 @@ def _abi_code(name):
 
 @pytest.mark.parametrize("ncol", [2, 48])
 def test_cuda_graph_step_is_bit_identical(cpl, cuda_device, ncol):
-    """CouplingPipeline.capture(): the replayed graph (K2 -> K1 -> projection -> K3) gives the bits of the eager step,
-    also after the inputs changed in place (new GCM profiles uploaded, LES volumes rewritten)."""
+    """CouplingPipeline.capture(): the replayed graph (K2 -> K1 -> K3 with its fused projection) gives the bits of the
+    eager step, also after the inputs changed in place (new GCM profiles uploaded, LES volumes rewritten)."""
     import torch
     from sp_coupler_b200 import synth
     from sp_coupler_b200.pipeline import CouplingPipeline
@@ -408,14 +411,16 @@ def test_cuda_graph_step_is_bit_identical(cpl, cuda_device, ncol):
             assert torch.equal(f1[k], f2[k]), k
         for k in ("prof", "cnt", "mask"):
             assert torch.equal(eager.slab[k], graphed.slab[k]), k
-    assert cpl.launches - l0 == 2 * 3 * 4      # both paths count K2, K1, projection, K3 per step
+    assert cpl.launches - l0 == 2 * 3 * 3      # both paths count K2, K1, K3 per step
 
 
-@pytest.mark.parametrize("nlev", [19, 91, 137])
-def test_compact_host_tendencies(cpl, cuda_device, nlev):
-    """step_host(compact=True): only the levels that can be non-zero travel back. The block equals the full result
-    from its first level on, everything above is exactly zero in the full result, and the host-side bound is at
-    most one level looser than the kernel's start_index."""
+@pytest.mark.parametrize("nlev,graph", [(19, False), (91, False), (91, True), (137, True)])
+def test_level_window_host_step(cpl, cuda_device, nlev, graph):
+    """The host-facing step on the live level window (pipeline.py, "Level window"): the GCM columns are cut off above
+    the first level over the LES top, only that window is uploaded, K3 itself stores the compact tendency block into
+    pinned host memory and raises the completion flag. The block equals the full-level result from lev0 on (bit for
+    bit), everything above lev0 is zero in the full result, the forcings are identical, and the host-side bound is
+    one level looser than the kernel's start_index."""
     import torch
     from sp_coupler_b200 import synth
     from sp_coupler_b200.pipeline import CouplingPipeline
@@ -423,18 +428,33 @@ def test_compact_host_tendencies(cpl, cuda_device, nlev):
     zf, zh = synth.les_grid(nk)
     gcm = synth.make_gcm_columns(ncol, nlev, seed=21, dtype=np.float32)
     aux = {k: torch.from_numpy(v).to(cuda_device) for k, v in synth.make_les_aux(ncol, nk, seed=21, dtype=np.float32).items()}
-    pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, torch.float32)
-    pipe.staging.fill_host(gcm)
-    pipe.staging.upload()
-    pipe.attach_les(synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=21), aux)
-    pipe.les_profiles()
-    _, full = pipe.step_host(900.0, 1.0, 1.0)
-    full = full.clone()
-    _, (live, first) = pipe.step_host(900.0, 1.0, 1.0, compact=True)
-    assert live.shape == (ncol, 7, nlev - first) and live.is_pinned() and live.is_contiguous()
-    assert torch.equal(live, full[:, :, first:])
-    assert not full[:, :, :first].any()
-    frc = pipe.forcings(900.0, 1.0)
-    tnd = cpl.les_to_gcm(pipe.gcm, pipe.zf, pipe.zh, pipe.slab, pipe.aux, frc["slab_idx"], 900.0, 1.0)
-    assert first == max(int(tnd["start_index"].min()) - 1, 0)
-    assert full[:, :, first + 1:].any()
+    vols = synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=21)
+    full_pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, torch.float32)
+    full_pipe.staging.fill_host(gcm)
+    full_pipe.staging.upload()
+    full_pipe.attach_les(vols, aux)
+    full_pipe.les_profiles()
+    win = CouplingPipeline(cpl, zf, zh, ncol, nlev, torch.float32)
+    win.attach_les(vols, aux)
+    win.les_profiles()
+    lev0 = win.stage_host(gcm)                     # picks the window, packs the cut columns into pinned staging
+    win.bind_host_output()                         # K3 -> pinned host memory + flag
+    assert win.nlw == nlev - lev0 and win.staging.nbytes < full_pipe.staging.nbytes or lev0 == 0
+    if graph:
+        win.staging.upload()
+        win.capture(900.0, 1.0, 1.0)
+    for it in range(3):
+        f_full, t_full = full_pipe.step_host(900.0, 1.0, 1.0)
+        t_full = t_full.clone()
+        f_win, t_win = win.step_host(900.0, 1.0, 1.0)
+        assert t_win.shape == (ncol, 7, nlev - lev0) and t_win.is_pinned() and t_win.is_contiguous()
+        assert torch.equal(t_win, t_full[:, :, lev0:]), it
+        assert not t_full[:, :, :lev0].any()
+        for k in ("f_u", "f_v", "f_thl", "f_qt", "f_ql", "f_ps", "ql_ref", "wthl", "wqt"):
+            assert torch.equal(f_full[k], f_win[k]), k
+        assert torch.equal(f_full["slab_idx"][:, :nlev - lev0], f_win["slab_idx"])
+        assert win.sync_error() == 0
+    frc = full_pipe.forcings(900.0, 1.0)
+    tnd = cpl.les_to_gcm(full_pipe.gcm, full_pipe.zf, full_pipe.zh, full_pipe.slab, full_pipe.aux, frc["slab_idx"], 900.0, 1.0)
+    assert lev0 == max(int(tnd["start_index"].min()) - 1, 0)
+    assert t_full[:, :, lev0 + 1:].any()

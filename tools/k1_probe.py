@@ -4,7 +4,10 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+# the sweep variants and the per-handle setter spc_tune_k1 exist only in the -DSPC_TUNING build (python -m sp_coupler_b200.build --tune)
+os.environ.setdefault("SPCPL_B200_LIB", os.path.join(ROOT, "sp_coupler_b200", "lib", "libspcpl_b200_tune.so"))
 import numpy as np
 import torch
 
@@ -39,7 +42,7 @@ if a.layout == "ijk":
 nbytes = sum(v.numel() * v.element_size() for v in vols)
 from sp_coupler_b200 import _abi
 for variant in [int(x) for x in a.variants.split(",")]:
-    _abi.lib().spc_tune_k1(variant)
+    _abi.lib().spc_tune_k1(cpl._h, variant)
     for _ in range(3):
         s = cpl.slab_reduce(vols, layout=a.layout, want_mask=not a.nomask)
     torch.cuda.synchronize()
@@ -55,8 +58,8 @@ for variant in [int(x) for x in a.variants.split(",")]:
     print("K1 variant %d %s ncol=%d %dx%dx%d %s mask=%s: median %.3f ms min %.3f ms -> %.1f GB/s (median) %.1f GB/s (best); %.0f col/s"
           % (variant, a.layout, a.ncol, a.nx, a.nx, a.nk, a.dtype, not a.nomask, np.median(ts), ts.min(),
              nbytes / np.median(ts) / 1e6, nbytes / ts.min() / 1e6, a.ncol / np.median(ts) * 1e3))
-_abi.lib().spc_tune_k1(0)
-_abi.lib().spc_tune_k1(100)
+_abi.lib().spc_tune_k1(cpl._h, 0)
+_abi.lib().spc_tune_k1(cpl._h, 100)
 # set_les_state write bandwidth
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 prof = torch.zeros((a.ncol, a.nk), dtype=torch.float64, device=dev)

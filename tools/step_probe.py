@@ -2,7 +2,10 @@
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+if len(sys.argv) > 4:   # the thread sweep needs spc_tune_profiles: only in the -DSPC_TUNING build (python -m sp_coupler_b200.build --tune)
+    os.environ.setdefault("SPCPL_B200_LIB", os.path.join(ROOT, "sp_coupler_b200", "lib", "libspcpl_b200_tune.so"))
 import numpy as np
 import torch
 
@@ -45,11 +48,11 @@ from sp_coupler_b200 import _abi
 frc = pipe.forcings(900.0, 1.0)
 if len(sys.argv) > 4:      # sweep of threads per column CTA for K2 / K3 (spc_tune_profiles)
     for th in [int(x) for x in sys.argv[4].split(",")]:
-        _abi.lib().spc_tune_profiles(0, 0, th)
+        _abi.lib().spc_tune_profiles(pipe.cpl._h, 0, 0, th)
         a, _ = t(lambda: pipe.forcings(900.0, 1.0))
         b, _ = t(lambda: pipe.tendencies(frc, 900.0, 1.0))
         print("threads %d: K2 %.1f us  projection+K3 %.1f us" % (th, a * 1e3, b * 1e3))
-    _abi.lib().spc_tune_profiles(0, 0, 0)
+    _abi.lib().spc_tune_profiles(pipe.cpl._h, 0, 0, 0)
 k2, frc = t(lambda: pipe.forcings(900.0, 1.0))
 k1, _ = t(lambda: pipe.les_profiles())
 k3, _ = t(lambda: pipe.tendencies(frc, 900.0, 1.0))
