@@ -33,6 +33,10 @@ import sys
 import tempfile
 import time
 
+import faulthandler
+
+faulthandler.enable()      # a rank that dies on a signal leaves a traceback instead of silence
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
