@@ -101,8 +101,36 @@ def make_sputils_golden():
     print("ref_sputils ->", len(blob), "arrays")
 
 
+def make_slabmean_golden():
+    """The ONLY statement of a horizontal slab average inside the reference tree, evaluated literally: the nudging code
+    forms `X[:, :, k].sum() / (itot * jtot)` over the (itot, jtot, ktot) view of a 3-D field (spcpl.py:621 for R,
+    spcpl.py:642,650 for max(qt - qsat, 0)), and `qt.std(axis=(0, 1))` (spcpl.py:741). DALES' own profile routines are
+    external, so this expression is what K1's slab means are pinned to; the above-threshold count is
+    `(ql[:, :, k] > thr).sum()`. Volumes are stored in the (i, j, k) view, float64 values that are exactly
+    representable in float32 (so the same fixture serves both storage types)."""
+    rng = np.random.default_rng(77)
+    itot, jtot, ktot = 16, 12, 32
+    prof = {"THL": 290.0 + 0.01 * np.arange(ktot), "QT": 0.008 * np.exp(-np.arange(ktot) / 10.0),
+            "U": 5.0 + 0.1 * np.arange(ktot), "V": -2.0 + 0.05 * np.arange(ktot)}
+    amp = {"THL": 0.1, "QT": 2.5e-5, "U": 0.5, "V": 0.5}
+    vol = {f: (prof[f][None, None, :] + amp[f] * rng.uniform(-1, 1, (itot, jtot, ktot))).astype(np.float32).astype(np.float64)
+           for f in prof}
+    qsat = prof["QT"][None, None, :] + 2.5e-5 * rng.uniform(-1.2, 1.2, ktot)[None, None, :]
+    vol["QL"] = np.maximum(vol["QT"] - qsat, 0).astype(np.float32).astype(np.float64)
+    blob = {}
+    for f, v in vol.items():
+        blob["vol_" + f] = v
+        blob["mean_" + f] = np.array([v[:, :, k].sum() / (itot * jtot) for k in range(ktot)])      # spcpl.py:642 form
+    blob["std_QT"] = vol["QT"].std(axis=(0, 1))                                                     # spcpl.py:741
+    for thr in (0.0, 1e-6):
+        blob["cnt_%g" % thr] = np.array([(vol["QL"][:, :, k] > thr).sum() for k in range(ktot)], dtype=np.int32)
+    np.savez_compressed(os.path.join(GOLDEN, "ref_slabmean.npz"), **blob)
+    print("ref_slabmean ->", len(blob), "arrays; cloudy cells per level", blob["cnt_0"])
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    make_slabmean_golden()
     make_sputils_golden()
     make_nudge_golden()
     for name, ncol, nlev, nk, seed, dt, fl, fg, cons in CASES:

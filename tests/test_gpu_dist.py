@@ -146,3 +146,97 @@ def test_sharded_step_equals_single_gpu(tmp_path, world):
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for rank in range(world):
         assert open(str(tmp_path / ("rank%d.txt" % rank))).read() == "ok", rank
+
+
+def _c5_worker(rank, world, port, outdir):
+    """BASELINE.json configs[4]: 16384 columns of 32x32x160, L137, float32, sharded over 8 GPUs (2048 per rank)."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    msgs = []
+    try:
+        from oracle import numpy_batched as nb
+        from sp_coupler_b200 import synth
+        from sp_coupler_b200.constants import TENDENCIES
+        from sp_coupler_b200.coupler import Coupler
+        from sp_coupler_b200.pipeline import CouplingPipeline
+        cpl = Coupler(dev)
+        ncol, nx, nk, nlev = 16384 // world, 32, 160, 137
+        ntot = ncol * world
+        zf, zh = synth.les_grid(nk)
+
+        def job(r, gather):
+            gcm = synth.make_gcm_columns(ncol, nlev, seed=46, dtype=np.float32, col0=r * ncol, ncol_total=ntot)
+            aux = synth.make_les_aux(ncol, nk, seed=46, dtype=np.float32, col0=r * ncol, ncol_total=ntot)
+            pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, torch.float32, gather=gather)
+            pipe.staging.fill_host(gcm)
+            pipe.staging.upload()
+            pipe.attach_les(synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=46, col0=r * ncol),
+                            {k: torch.from_numpy(v).to(dev) for k, v in aux.items()})
+            pipe.les_profiles()
+            return pipe, gcm, aux
+
+        pipe, gcm, aux = job(rank, "p2p-owner")
+        pipe.capture(900.0, 1.0, 1.0)
+        for _ in range(2):
+            pipe.step(900.0, 1.0, 1.0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if pipe.sync_error():
+            msgs.append("sync error %d" % pipe.sync_error())
+        # every rank: one of ITS columns against the CPU oracle on host-generated inputs (bit-identical generator)
+        c = (37 * (rank + 1)) % ncol
+        g1 = {k: v[c:c + 1] for k, v in gcm.items()}
+        a1 = {k: v[c:c + 1] for k, v in aux.items()}
+        hv = synth.make_les_volumes(g1, zf, nx, nx, seed=46, dtype=np.float32, col0=rank * ncol + c)
+        ref = nb.coupling_step(g1, zf, zh, hv, a1, a1["PS"], 900.0, 1.0, 1.0, True)
+        got = pipe.tend[c].cpu().numpy()
+        for i, k in enumerate(TENDENCIES):
+            d = np.abs(got[i] - ref["tendencies"][k][0]).max() / max(np.abs(ref["tendencies"][k][0]).max(), 1e-300)
+            if d > 1e-4:
+                msgs.append("rank %d column %d %s: rel err %.2e vs the oracle" % (rank, c, k, d))
+        if not np.array_equal(pipe.slab["cnt"][c].cpu().numpy(), ref["cnt"][0]):
+            msgs.append("rank %d column %d: cloud counts differ from the oracle" % (rank, c))
+        if rank == 0:       # sharding invariance: the gathered block == the owner's own computation of every rank's columns
+            gathered = pipe.tend_all.clone()
+            for r in range(world):
+                sp, _, _ = job(r, False)
+                sp.step_device(900.0, 1.0, 1.0)
+                torch.cuda.synchronize()
+                if not torch.equal(sp.tend, gathered[r * ncol:(r + 1) * ncol]):
+                    msgs.append("block of rank %d: gathered bits differ from the single-GPU computation" % r)
+                del sp
+                torch.cuda.empty_cache()
+        dist.barrier()
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        msgs.append("rank %d raised: %s\n%s" % (rank, e, traceback.format_exc()))
+    open(os.path.join(outdir, "rank%d.txt" % rank), "w").write("\n".join(msgs) if msgs else "ok")
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:           # noqa: BLE001
+        pass
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_c5_sharded_over_8_gpus(tmp_path):
+    """16384 columns over 8 GPUs: a spot column per rank against the oracle, and the block gathered on the GCM owner
+    (K3's NVLink stores, graph-replayed step) equal to the owner's own single-GPU computation of every rank's columns."""
+    import torch
+    import torch.multiprocessing as mp
+    world = 8
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip("needs 8 GPUs on the box")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_c5_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        assert open(str(tmp_path / ("rank%d.txt" % rank))).read() == "ok", rank

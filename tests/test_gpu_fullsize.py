@@ -93,6 +93,47 @@ def _run_config(cpl, dev, ncol, nx, nk, nlev, spots, chunk):
     torch.cuda.empty_cache()
 
 
+def test_c2_full_size_every_column_fp64(cpl, cuda_device):
+    """BASELINE.json configs[1] at full size: 128 columns, 64x64x160, L91, float64 - the fp64 equivalence run. The
+    inputs of EVERY column are generated on the host (3.4 GB), the CPU oracle computes every column, and every column of
+    the device step is compared: counts, projected counts, bracket / slab indices and start_index exact; slab means,
+    forcings and tendencies within the north star's fp64 tolerance 1e-6 (measured ~1e-12)."""
+    ncol, nx, nk, nlev = 128, 64, 160, 91
+    zf, zh = synth.les_grid(nk)
+    gcm = synth.make_gcm_columns(ncol, nlev, seed=43, dtype=np.float64)
+    aux = synth.make_les_aux(ncol, nk, seed=43, dtype=np.float64)
+    hv = synth.make_les_volumes(gcm, zf, nx, nx, seed=43, dtype=np.float64)
+    ref = nb.coupling_step(gcm, zf, zh, hv, aux, aux["PS"], 900.0, 1.0, 1.0, True)
+    dev = cuda_device
+    vols = [torch.from_numpy(hv[f]).to(dev) for f in LES_FIELDS]
+    gen = synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=43, dtype=torch.float64)
+    for a, b, f in zip(vols, gen, LES_FIELDS):                     # device generator == host generator, all columns
+        assert torch.equal(a, b), f
+    del gen
+    d_gcm = {k: torch.from_numpy(v).to(dev) for k, v in gcm.items()}
+    d_aux = {k: torch.from_numpy(v).to(dev) for k, v in aux.items()}
+    d_zf, d_zh = torch.from_numpy(zf).to(dev), torch.from_numpy(zh).to(dev)
+    slab = cpl.slab_reduce(vols)
+    frc = cpl.gcm_to_les(d_gcm, d_zf, d_zh, slab["prof"], d_aux["PS"], 900.0, 1.0, True, want_bracket=True)
+    tnd = cpl.les_to_gcm(d_gcm, d_zf, d_zh, slab, d_aux, frc["slab_idx"], 900.0, 1.0, diagnostics=True)
+    assert np.array_equal(n(slab["cnt"]), ref["cnt"])
+    assert np.array_equal(n(tnd["cntslab"]), ref["cntslab"])
+    assert np.array_equal(n(frc["bracket"]), ref["forcings"]["bracket"])
+    assert np.array_equal(n(frc["slab_idx"]), ref["slab_idx"])
+    assert np.array_equal(n(tnd["bracket"]), ref["tendencies"]["bracket"])
+    assert np.array_equal(n(tnd["start_index"]), ref["tendencies"]["start_index"])
+    worst = 0.0
+    for c in range(ncol):                                          # per column, per variable: max|a-b| / max|ref|
+        for f, name in enumerate(LES_FIELDS):
+            worst = max(worst, relerr(n(slab["prof"][f, c]), ref["prof"][name][c]))
+        for k in ("f_u", "f_v", "f_thl", "f_qt", "f_ql"):
+            worst = max(worst, relerr(n(frc[k][c]), ref["forcings"][k][c]))
+        for k in TENDENCIES:
+            worst = max(worst, relerr(n(tnd[k][c]), ref["tendencies"][k][c]))
+    assert worst <= 1e-6, worst
+    assert worst <= 1e-10, worst      # what the float64 path actually delivers
+
+
 def test_c3_full_size(cpl, cuda_device):
     """2048 columns, 64x64x160, L91, float32 (26.8 GB)."""
     _run_config(cpl, cuda_device, 2048, 64, 160, 91, spots=(0, 1023, 2047), chunk=64)

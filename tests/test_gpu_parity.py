@@ -458,3 +458,22 @@ def test_level_window_host_step(cpl, cuda_device, nlev, graph):
     tnd = cpl.les_to_gcm(full_pipe.gcm, full_pipe.zf, full_pipe.zh, full_pipe.slab, full_pipe.aux, frc["slab_idx"], 900.0, 1.0)
     assert lev0 == max(int(tnd["start_index"].min()) - 1, 0)
     assert t_full[:, :, lev0 + 1:].any()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_slab_reduce_matches_the_reference_held_expression(cpl, cuda_device, dtype):
+    """a1/a2 pin: K1 against `X[:, :, k].sum() / (itot * jtot)` (the one slab average written in the reference tree,
+    spcpl.py:621,642,650; fixture tests/golden/ref_slabmean.npz) in both memory layouts; counts exact for two thresholds."""
+    import os
+    import torch
+    import conftest
+    z = np.load(os.path.join(conftest.GOLDEN, "ref_slabmean.npz"))
+    fields = ("THL", "QT", "QL", "U", "V")
+    ijk = [torch.from_numpy(np.ascontiguousarray(z["vol_" + f].astype(dtype)[None])).to(cuda_device) for f in fields]
+    kji = [v.permute(0, 3, 2, 1).contiguous() for v in ijk]
+    for layout, vols in (("ijk", ijk), ("kji", kji)):
+        for thr in (0.0, 1e-6):
+            slab = cpl.slab_reduce(vols, layout=layout, ql_thresh=thr, want_mask=True)
+            assert np.array_equal(n(slab["cnt"][0]), z["cnt_%g" % thr]), (layout, thr)
+        for i, f in enumerate(fields):
+            assert relerr(n(slab["prof"][i, 0]), z["mean_" + f]) <= 1e-12, (f, layout)

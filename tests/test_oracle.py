@@ -188,3 +188,20 @@ def test_oracle_integrals_match_reference_golden():
             if not np.isnan(weighted):
                 assert nb.integral(a, b, edges, q[0], rho[0]) == weighted
         assert nb.integral_plain(-1.0, 10.0, edges, q[0]) is None          # end point outside the range: sputils.py:113-115
+
+
+def test_slab_mean_matches_the_reference_held_expression():
+    """a1/a2 pin: the only slab average written inside the reference tree is
+    `X[:, :, k].sum() / (itot * jtot)` over the (itot, jtot, ktot) view (spcpl.py:621,642,650). The fixture evaluates
+    that expression literally (oracle/make_golden.py::make_slabmean_golden); the oracle's slab_reduce must agree in
+    both memory layouts, for both storage types, and the counts must be exact."""
+    z = np.load(os.path.join(GOLDEN, "ref_slabmean.npz"))
+    for dt in (np.float64, np.float32):
+        ijk = {f: z["vol_" + f].astype(dt)[None] for f in ("THL", "QT", "QL", "U", "V")}          # [1][nx][ny][nk]
+        kji = {f: np.ascontiguousarray(np.transpose(v, (0, 3, 2, 1))) for f, v in ijk.items()}     # [1][nk][ny][nx]
+        for layout, vols in ((1, ijk), (0, kji)):
+            for thr in (0.0, 1e-6):
+                prof, cnt = nb.slab_reduce(vols, thr, layout)
+                assert np.array_equal(cnt[0], z["cnt_%g" % thr])
+            for f in vols:
+                assert relerr(prof[f][0], z["mean_" + f]) <= 1e-15, (f, layout, dt)
