@@ -60,7 +60,10 @@ struct K2Args {
   int nk, couple_surface;
 };
 
-template <typename T>
+// PREFETCH: request the operands of the thread's first LES level before phase 1 (a shorter dependent chain, 14 more
+// registers): pays when the launch is a single wave of CTAs, i.e. latency-bound; larger launches are bound by the number of
+// resident CTAs and run the leaner variant.
+template <typename T, bool PREFETCH>
 __global__ void __launch_bounds__(kThreads) gcm_to_les_kernel(const K2Args a) {
   extern __shared__ __align__(16) double sm[];
   const int nlev = a.g.nlev, nk = a.nk, ncol = a.g.ncol;
@@ -76,6 +79,17 @@ __global__ void __launch_bounds__(kThreads) gcm_to_les_kernel(const K2Args a) {
   const double zs = ld<T>(a.g.Zghalf, bh + nlev);   // Zghalf[-1]
   const spc_les_forcing& o = a.o;
   const bool want_idx = o.slab_idx && a.zh;         // block-uniform
+  // operands of this thread's first LES level (phase 2) are requested now, so that they are in flight during phase 1
+  const size_t pf = (size_t)ncol * nk;   // field stride of les_prof [5][ncol][nk]
+  const int k_first = threadIdx.x;
+  double x_first = 0.0, lp_first[SPC_NFIELDS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (PREFETCH && k_first < nk) {
+    x_first = __ldg(a.zf + k_first);
+    if (a.les_prof) {
+#pragma unroll
+      for (int f = 0; f < SPC_NFIELDS; ++f) lp_first[f] = __ldg(a.les_prof + f * pf + (size_t)c * nk + k_first);
+    }
+  }
   if (want_idx) {
     for (int k = threadIdx.x; k < nk; k += blockDim.x) zh_s[k] = __ldg(a.zh + k);
     __syncthreads();
@@ -124,9 +138,9 @@ __global__ void __launch_bounds__(kThreads) gcm_to_les_kernel(const K2Args a) {
   }
   __syncthreads();
 
-  const size_t pf = (size_t)ncol * nk;   // field stride of les_prof [5][ncol][nk]
   for (int k = threadIdx.x; k < nk; k += blockDim.x) {
-    const double x = __ldg(a.zf + k);
+    const bool first = PREFETCH && (k == k_first);
+    const double x = first ? x_first : __ldg(a.zf + k);
     const int j = upper_bound(Zf, nlev, x) - 1;
     const size_t i = (size_t)c * nk + k;
     const double thl_g = interp_at(Zf, thl, nlev, x, j);
@@ -141,11 +155,14 @@ __global__ void __launch_bounds__(kThreads) gcm_to_les_kernel(const K2Args a) {
     st<T>(o.v, i, v_g);
     st<T>(o.ql_ref, i, ql_g);
     if (a.les_prof) {                                                    // spcpl.py:328-333
-      st<T>(o.f_u, i, a.factor * (u_g - __ldg(a.les_prof + SPC_U * pf + i)) / a.dt);
-      st<T>(o.f_v, i, a.factor * (v_g - __ldg(a.les_prof + SPC_V * pf + i)) / a.dt);
-      st<T>(o.f_thl, i, a.factor * (thl_g - __ldg(a.les_prof + SPC_THL * pf + i)) / a.dt);
-      st<T>(o.f_qt, i, a.factor * (qt_g - __ldg(a.les_prof + SPC_QT * pf + i)) / a.dt);
-      st<T>(o.f_ql, i, a.factor * (ql_g - __ldg(a.les_prof + SPC_QL * pf + i)) / a.dt);
+      double lp[SPC_NFIELDS];
+#pragma unroll
+      for (int f = 0; f < SPC_NFIELDS; ++f) lp[f] = first ? lp_first[f] : __ldg(a.les_prof + f * pf + i);
+      st<T>(o.f_u, i, a.factor * (u_g - lp[SPC_U]) / a.dt);
+      st<T>(o.f_v, i, a.factor * (v_g - lp[SPC_V]) / a.dt);
+      st<T>(o.f_thl, i, a.factor * (thl_g - lp[SPC_THL]) / a.dt);
+      st<T>(o.f_qt, i, a.factor * (qt_g - lp[SPC_QT]) / a.dt);
+      st<T>(o.f_ql, i, a.factor * (ql_g - lp[SPC_QL]) / a.dt);
     }
   }
 }
@@ -515,7 +532,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 //             stored into the packed block and into every remote target (peer GPUs over NVLink / pinned host memory)
 //   epilogue  (sync) last CTA of the launch: signal flags, wait for the peers, advance the epoch
 template <typename T>
-__global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
+__global__ void __launch_bounds__(kThreads, 4) les_to_gcm_kernel(const K3Args a) {
   extern __shared__ __align__(16) double sm[];
   const int nlev = a.g.nlev, nk = a.nk, ncol = a.g.ncol;
   const int c = blockIdx.x;
@@ -532,7 +549,14 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
   double* rho = v_d + nk;        // [nk]   (conservative only)
   double* ZhD = rho + nk;        // [nlev+1] descending half-level heights (conservative only)
   double* zh_s = ZhD + nlev + 1; // [nk]   LES half levels (conservative only)
-  int* cs_sh = reinterpret_cast<int*>(zh_s + nk);   // [nlev] projected cloud counts, ascending slabs (fused projection)
+  double* gT = zh_s + nk;        // 7 GCM profiles [nlev] each, GCM order (the X of f_X = factor (x_les - X) / dt)
+  double* gSH = gT + nlev;
+  double* gQL = gSH + nlev;
+  double* gQI = gQL + nlev;
+  double* gU = gQI + nlev;
+  double* gV = gU + nlev;
+  double* gA = gV + nlev;
+  int* cs_sh = reinterpret_cast<int*>(gA + nlev);   // [nlev] projected cloud counts, ascending slabs (fused projection)
   int* kend = cs_sh + nlev;      // [nlev], [nk], [nlev]: scratch of the projection prologue
   int* live_k = kend + nlev;
   int* queue = live_k + nk;
@@ -545,20 +569,19 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
   const size_t pfs = (size_t)ncol * nk;
   if (a.sync && threadIdx.x == 0) s_epoch = a.sync[SPC_SYNC_EPOCH];   // only this launch's last CTA changes it, at the very end
 
-  // cloud fraction source: given A | counts projected here from the KJI mask | counts written to o.cntslab by the
-  // IJK projection kernel launched just before | none
-  const bool fused = a.project_mw > 0;
-  const bool from_global = !fused && (a.les.A == nullptr) && a.les.mask && o.cntslab;
-  if (fused) {
-    const int nq = cloud_slab_queue<T>(a.les.slab_idx, a.les.cnt, nk, nlev, c, kend, live_k, queue, o.cntslab, (T*)nullptr, cs_sh);
-    const bool vec = (a.project_mw & 3) == 0 && (reinterpret_cast<uintptr_t>(a.les.mask) & 15) == 0;
-    project_kji_queued<T>(a.les.mask + (size_t)c * nk * a.project_mw, vec, a.project_mw, nq, queue, kend, live_k, nlev, c,
-                          1.0, o.cntslab, (T*)nullptr, cs_sh);
-  }
-
+  // Stage every profile the column needs into shared memory first: all these global loads are independent and in flight
+  // together (one memory latency), and the level loop further down runs out of shared memory only; the projection
+  // prologue in between has its own chain of dependent loads (counts -> slab ranges -> mask rows).
   for (int l = threadIdx.x; l < nlev; l += blockDim.x) {
     ZfA[nlev - 1 - l] = (ld<T>(a.g.Zgfull, b + l) - zs) / grav;         // les.gcm_Zf, spcpl.py:198,390
     PfA[nlev - 1 - l] = ld<T>(a.g.Pfull, b + l);
+    gT[l] = ld<T>(a.g.T, b + l);
+    gSH[l] = ld<T>(a.g.SH, b + l);
+    gQL[l] = ld<T>(a.g.QL, b + l);
+    gQI[l] = ld<T>(a.g.QI, b + l);
+    gU[l] = ld<T>(a.g.U, b + l);
+    gV[l] = ld<T>(a.g.V, b + l);
+    gA[l] = ld<T>(a.g.A, b + l);
   }
   if (a.conservative)
     for (int l = threadIdx.x; l <= nlev; l += blockDim.x) ZhD[l] = (ld<T>(a.g.Zghalf, bh + l) - zs) / grav;
@@ -578,6 +601,17 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
       rho[k] = ld<T>(a.les.Rhobf, i);
       zh_s[k] = __ldg(a.zh + k);
     }
+  }
+
+  // cloud fraction source: given A | counts projected here from the KJI mask | counts written to o.cntslab by the
+  // IJK projection kernel launched just before | none
+  const bool fused = a.project_mw > 0;
+  const bool from_global = !fused && (a.les.A == nullptr) && a.les.mask && o.cntslab;
+  if (fused) {
+    const int nq = cloud_slab_queue<T>(a.les.slab_idx, a.les.cnt, nk, nlev, c, kend, live_k, queue, o.cntslab, (T*)nullptr, cs_sh);
+    const bool vec = (a.project_mw & 3) == 0 && (reinterpret_cast<uintptr_t>(a.les.mask) & 15) == 0;
+    project_kji_queued<T>(a.les.mask + (size_t)c * nk * a.project_mw, vec, a.project_mw, nq, queue, kend, live_k, nlev, c,
+                          1.0, o.cntslab, (T*)nullptr, cs_sh);
   }
   __syncthreads();
 
@@ -638,13 +672,13 @@ __global__ void __launch_bounds__(kThreads) les_to_gcm_kernel(const K3Args a) {
     }
     const double ft = a.dt;                      // spcpl.py:427
     double f[SPC_NTEND];
-    f[SPC_F_T] = a.factor * (val[0] - ld<T>(a.g.T, i)) / ft;               // spcpl.py:518
-    f[SPC_F_SH] = a.factor * ((val[1] - val[2]) - ld<T>(a.g.SH, i)) / ft;  // spcpl.py:519
-    f[SPC_F_QL] = a.factor * (val[3] - ld<T>(a.g.QL, i)) / ft;             // spcpl.py:520
-    f[SPC_F_QI] = a.factor * (val[4] - ld<T>(a.g.QI, i)) / ft;             // spcpl.py:521
-    f[SPC_F_U] = a.factor * (val[5] - ld<T>(a.g.U, i)) / ft;               // spcpl.py:524
-    f[SPC_F_V] = a.factor * (val[6] - ld<T>(a.g.V, i)) / ft;               // spcpl.py:525
-    f[SPC_F_A] = a.factor * (A_d - ld<T>(a.g.A, i)) / ft;                  // spcpl.py:526
+    f[SPC_F_T] = a.factor * (val[0] - gT[l]) / ft;               // spcpl.py:518
+    f[SPC_F_SH] = a.factor * ((val[1] - val[2]) - gSH[l]) / ft;  // spcpl.py:519
+    f[SPC_F_QL] = a.factor * (val[3] - gQL[l]) / ft;             // spcpl.py:520
+    f[SPC_F_QI] = a.factor * (val[4] - gQI[l]) / ft;             // spcpl.py:521
+    f[SPC_F_U] = a.factor * (val[5] - gU[l]) / ft;               // spcpl.py:524
+    f[SPC_F_V] = a.factor * (val[6] - gV[l]) / ft;               // spcpl.py:525
+    f[SPC_F_A] = a.factor * (A_d - gA[l]) / ft;                  // spcpl.py:526
     const bool above = l < s_start;              // spcpl.py:527-533: f[0:start_index] *= 0
 #pragma unroll
     for (int n = 0; n < SPC_NTEND; ++n) {
@@ -824,8 +858,14 @@ int spc_gcm_to_les(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   a.dt = dt; a.factor = factor; a.nk = nk; a.couple_surface = couple_surface;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int threads = column_threads(h->k2_threads, std::max(gcm->nlev + 1, nk));
-  if (gcm->dtype == SPC_F32) gcm_to_les_kernel<float><<<gcm->ncol, threads, smem, st>>>(a);
-  else gcm_to_les_kernel<double><<<gcm->ncol, threads, smem, st>>>(a);
+  const bool one_wave = gcm->ncol <= 6 * h->num_sms;
+  if (gcm->dtype == SPC_F32) {
+    if (one_wave) gcm_to_les_kernel<float, true><<<gcm->ncol, threads, smem, st>>>(a);
+    else gcm_to_les_kernel<float, false><<<gcm->ncol, threads, smem, st>>>(a);
+  } else {
+    if (one_wave) gcm_to_les_kernel<double, true><<<gcm->ncol, threads, smem, st>>>(a);
+    else gcm_to_les_kernel<double, false><<<gcm->ncol, threads, smem, st>>>(a);
+  }
   SPC_CUDA(cudaGetLastError());
   return SPC_OK;
 }
@@ -870,8 +910,9 @@ int spc_les_to_gcm(spc_handle h, const spc_gcm_cols* gcm, const double* zf, cons
   }
   SPC_REQUIRE(!(out->sync && gcm->ncol == 0), SPC_ERR_ARG, "spc_les_to_gcm: the completion protocol needs at least one column per rank");
   if (gcm->ncol == 0) return SPC_OK;
-  // doubles: ZfA, PfA [nlev] | zf + 7 profiles + rho [9 nk] | ZhD [nlev+1] | zh [nk];  ints: cs, kend, queue [nlev], live_k [nk]
-  const size_t smem = ((size_t)3 * gcm->nlev + 1 + (size_t)10 * nk) * sizeof(double) + ((size_t)3 * gcm->nlev + nk) * sizeof(int);
+  // doubles: ZfA, PfA [nlev] | zf + 7 profiles + rho [9 nk] | ZhD [nlev+1] | zh [nk] | 7 GCM profiles [7 nlev]
+  // ints: cs, kend, queue [nlev], live_k [nk]
+  const size_t smem = ((size_t)10 * gcm->nlev + 1 + (size_t)10 * nk) * sizeof(double) + ((size_t)3 * gcm->nlev + nk) * sizeof(int);
   SPC_REQUIRE(smem <= 48 * 1024, SPC_ERR_UNSUPPORTED, "spc_les_to_gcm: nlev=%d, nk=%d too large", gcm->nlev, nk);
   spc::DeviceGuard guard(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);

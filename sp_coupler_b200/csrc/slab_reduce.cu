@@ -16,6 +16,8 @@
 //   slab_reduce_generic_kernel<T>          KJI, any other slab size / alignment (one warp per slab, scalar loads)
 //   slab_reduce_ijk_tma_kernel<T, SLOTS>   IJK (k fastest), per-warp TMA rings over whole (field, column) items
 //   slab_reduce_ijk_kernel<T, VEC>         IJK, shapes outside the TMA plan (one CTA per item)
+#include <math.h>
+
 #include <type_traits>
 
 #include "spc_common.cuh"
@@ -43,6 +45,7 @@ struct K1Args {
   int32_t* cnt;
   uint32_t* mask;
   double thr;
+  float thr_f;          // smallest float32 x with (double)x > thr (NaN if none): x >= thr_f  <=>  (double)x > thr, exactly
   long long per_field;  // ncol*nk slabs per field
   long long total;      // 5*ncol*nk
   int S;                // elements per slab
@@ -519,9 +522,10 @@ __global__ void __launch_bounds__(1024) slab_reduce_ijk_kernel(const K1Args a, i
 // levels in a fixed order (bit-reproducible, no atomics on data) the next time it looks. No block-wide
 // barrier in the steady state. Items are numbered column-major (item = c*5 + f) so that at any moment the
 // SMs are spread over all five fields and the heavier ql items (count + mask) overlap with the others.
-template <int WARPS_, int CHUNK_, int BATCH5_ = 2>
+template <int WARPS_, int CHUNK_, int BATCH5_ = 2, int STAGES_ = 1>
 struct IjkRing {
   static constexpr int kWarps = WARPS_, kChunk = CHUNK_, kBatch5 = BATCH5_;  // kBatch5: periods per pass when SLOTS >= 4
+  static constexpr int kStages = STAGES_;   // ring stages per warp: > 1 keeps a copy in flight while the warp reduces a chunk
 };
 
 struct IjkArgs {
@@ -597,6 +601,88 @@ __device__ __forceinline__ void ijk_periods(const uint8_t* pb, int lane, double 
   }
 }
 
+// Transpose of an NL x NL matrix of EB-bit elements held one row per lane by NL consecutive lanes (NL * EB == 32):
+// afterwards element i of lane j is what element j of lane i was. log2(NL) butterfly stages of one shuffle each.
+template <int NL, int EB>
+__device__ __forceinline__ uint32_t lane_transpose_bits(uint32_t x, int lane) {
+  static_assert(NL * EB == 32, "one 32-bit word per lane");
+#pragma unroll
+  for (int s = 0; (1 << s) < NL; ++s) {
+    const int d = 1 << s, sh = EB << s;
+    // elements whose index has bit s clear: runs of sh ones alternating with runs of sh zeros
+    const uint32_t m = sh == 2 ? 0x33333333u : sh == 4 ? 0x0F0F0F0Fu : sh == 8 ? 0x00FF00FFu : 0x0000FFFFu;
+    const uint32_t y = __shfl_xor_sync(kFull, x, d);
+    x = (lane & d) ? (((y >> sh) & m) | (x & ~m)) : ((x & m) | ((y & m) << sh));
+  }
+  return x;
+}
+
+// The ql chunk with the per-point cloud mask. A mask word (32 levels of one horizontal point) is spread over the NL =
+// 32 / VEC lanes that hold the point's vectors in ONE load, so assembling it per load costs a log2(NL)-step shuffle
+// butterfly for every vector (the round-1 form: 3 dependent shuffles per float4). Here every lane instead collects
+// its own VEC flag bits of up to NL consecutive loads in a private word (compile-time bit positions), and one NL x NL
+// bit-block transpose across the lane group turns the private words into the natural mask words of those loads:
+// log2(NL) shuffles per group of loads, and the lanes then store consecutive words. Same mask bits, same layout.
+// The groups are cut at compile time inside a batch of UU periods (UU * SLOTS loads): full groups of NL, then the rest.
+template <typename T, int SLOTS, int UU>
+__device__ __forceinline__ void ijk_periods_mask(const uint8_t* pb, int lane, double thr, float thr_f, uint32_t* mw0,
+                                                 double (&acc)[SLOTS][16 / sizeof(T)], int (&cnt)[SLOTS][16 / sizeof(T)]) {
+  constexpr int VEC = 16 / (int)sizeof(T), NL = 32 / VEC, P = SLOTS * 32, NLOADS = UU * SLOTS;
+  using V = std::conditional_t<sizeof(T) == 4, float4, double2>;
+  V v[UU][SLOTS];
+#pragma unroll
+  for (int u = 0; u < UU; ++u)
+#pragma unroll
+    for (int it = 0; it < SLOTS; ++it) v[u][it] = reinterpret_cast<const V*>(pb)[u * P + it * 32 + lane];
+  uint32_t W = 0u;
+#pragma unroll
+  for (int t = 0; t < NLOADS; ++t) {           // load t of the batch = period t / SLOTS, slot t % SLOTS
+    const int u = t / SLOTS, it = t % SLOTS;   // compile-time after unrolling
+    uint32_t nib;
+    if constexpr (sizeof(T) == 4) {
+      const double d0 = (double)v[u][it].x, d1 = (double)v[u][it].y, d2 = (double)v[u][it].z, d3 = (double)v[u][it].w;
+      acc[it][0] += d0;
+      acc[it][1] += d1;
+      acc[it][2] += d2;
+      acc[it][3] += d3;
+      const uint32_t b0 = v[u][it].x >= thr_f, b1 = v[u][it].y >= thr_f, b2 = v[u][it].z >= thr_f, b3 = v[u][it].w >= thr_f;
+      cnt[it][0] += b0;
+      cnt[it][1] += b1;
+      cnt[it][2] += b2;
+      cnt[it][3] += b3;
+      nib = b0 | (b1 << 1) | (b2 << 2) | (b3 << 3);
+    } else {
+      acc[it][0] += v[u][it].x;
+      acc[it][1] += v[u][it].y;
+      const uint32_t b0 = v[u][it].x > thr, b1 = v[u][it].y > thr;
+      cnt[it][0] += b0;
+      cnt[it][1] += b1;
+      nib = b0 | (b1 << 1);
+    }
+    W |= nib << (VEC * (t % NL));
+    if ((t % NL) == NL - 1 || t == NLOADS - 1) {          // compile-time: a group of (t % NL) + 1 loads is complete
+      const int t0 = t - (t % NL), n = (t % NL) + 1;
+      const uint32_t x = lane_transpose_bits<NL, VEC>(W, lane);
+      if (n == NL || (lane & (NL - 1)) < n) mw0[(t0 + (lane & (NL - 1))) * VEC + lane / NL] = x;   // VEC = 32 / NL words per load
+      W = 0u;
+    }
+  }
+}
+
+template <typename T, int SLOTS, int BATCH5>
+__device__ __forceinline__ void ijk_chunk_mask(const uint8_t* buf, int nper, int lane, double thr, float thr_f, uint32_t* mw0,
+                                               double (&acc)[SLOTS][16 / sizeof(T)], int (&cnt)[SLOTS][16 / sizeof(T)]) {
+  constexpr int VEC = 16 / (int)sizeof(T), P = SLOTS * 32;
+  constexpr int kBatch = SLOTS >= 4 ? BATCH5 : 8 / SLOTS;
+  int p = 0;                     // period cursor; a period is SLOTS loads = SLOTS * VEC mask words
+#pragma unroll 1
+  for (; p + kBatch <= nper; p += kBatch)
+    ijk_periods_mask<T, SLOTS, kBatch>(buf + (size_t)p * (P * 16), lane, thr, thr_f, mw0 + (size_t)p * SLOTS * VEC, acc, cnt);
+#pragma unroll 1
+  for (; p < nper; ++p)
+    ijk_periods_mask<T, SLOTS, 1>(buf + (size_t)p * (P * 16), lane, thr, thr_f, mw0 + (size_t)p * SLOTS * VEC, acc, cnt);
+}
+
 template <typename T, int SLOTS, int BATCH5, bool QL, bool MASK>
 __device__ __forceinline__ void ijk_chunk(const uint8_t* buf, int nper, int lane, double thr, uint32_t* mw,
                                           double (&acc)[SLOTS][16 / sizeof(T)], int (&cnt)[SLOTS][16 / sizeof(T)]) {
@@ -613,30 +699,32 @@ __device__ __forceinline__ void ijk_chunk(const uint8_t* buf, int nper, int lane
 
 template <typename T, int SLOTS, typename R>
 __global__ void __launch_bounds__(R::kWarps * 32, 1) slab_reduce_ijk_tma_kernel(const K1Args a, const IjkArgs g) {
-  constexpr int kWarps = R::kWarps, kChunk = R::kChunk;
+  constexpr int kWarps = R::kWarps, kChunk = R::kChunk, kStages = R::kStages;
   constexpr int VEC = 16 / (int)sizeof(T);     // levels per vector
   constexpr int LPW = 32 / VEC;                // lanes that share one 32-level mask word
   constexpr int P = SLOTS * 32;                // vectors per period
   extern __shared__ __align__(128) uint8_t smem[];
-  // [kWarps][kChunk] ring | [kWarps][P][VEC] double partial sums | [kWarps][P][VEC] int partial counts | mbarriers | flags
-  double* psum = reinterpret_cast<double*>(smem + (size_t)kWarps * kChunk);
+  // [kWarps][kStages][kChunk] ring | [kWarps][P][VEC] double partial sums | [kWarps][P][VEC] int partial counts |
+  // [kWarps][kStages] mbarriers | flags
+  double* psum = reinterpret_cast<double*>(smem + (size_t)kWarps * kStages * kChunk);
   int* pcnt = reinterpret_cast<int*>(psum + (size_t)kWarps * P * VEC);
   uint64_t* bars = reinterpret_cast<uint64_t*>(pcnt + (size_t)kWarps * P * VEC);
-  unsigned int* sync = reinterpret_cast<unsigned int*>(bars + kWarps);   // [0] partials parked, [1] level slices combined
+  unsigned int* sync = reinterpret_cast<unsigned int*>(bars + kWarps * kStages);   // [0] partials parked, [1] level slices combined
   volatile unsigned int* vsync = sync;
   // the shuffle tells the compiler that the warp index is warp-uniform, so every branch below that depends on the
   // warp's item / chunk cursor is uniform too and the mask shuffles need no re-convergence wrappers
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  uint8_t* wbuf = smem + (size_t)warp * kChunk;
+  uint8_t* wbuf = smem + (size_t)warp * kStages * kChunk;
   const uint32_t wbuf_s = smem_u32(wbuf);
-  const uint32_t bar = smem_u32(bars + warp);
+  const uint32_t bar0 = smem_u32(bars + warp * kStages);
 
   if (threadIdx.x == 0) {
     sync[0] = 0u;
     sync[1] = 0u;
   }
   if (lane == 0) {
-    mbar_init(bar, 1);
+#pragma unroll
+    for (int sgi = 0; sgi < kStages; ++sgi) mbar_init(bar0 + 8 * sgi, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -654,21 +742,26 @@ __global__ void __launch_bounds__(R::kWarps * 32, 1) slab_reduce_ijk_tma_kernel(
     pj -= g.nch;
     ++pio;
   }
-  auto issue = [&]() {
+  auto issue = [&](int stage) {
     const unsigned int item = blockIdx.x + (unsigned int)pio * gridDim.x;
     const unsigned int c = item / SPC_NFIELDS;
     const int f = (int)(item - c * SPC_NFIELDS);
     const uint8_t* src = static_cast<const uint8_t*>(field_ptr(a, f)) + (size_t)c * g.item_bytes + (size_t)pj * g.chunk_bytes;
     const uint32_t bytes = (uint32_t)min((long long)g.chunk_bytes, g.item_bytes - (long long)pj * g.chunk_bytes);
+    const uint32_t bar = bar0 + 8 * stage;
     mbar_arrive_expect_tx(bar, bytes);
-    tma_bulk_g2s(wbuf_s, src, bytes, bar, pol);
+    tma_bulk_g2s(wbuf_s + stage * kChunk, src, bytes, bar, pol);
     pj += kWarps;
     while (pj >= g.nch && pio < my_items) {
       pj -= g.nch;
       ++pio;
     }
   };
-  if (lane == 0 && pio < my_items) issue();
+  if (lane == 0) {
+#pragma unroll
+    for (int sgi = 0; sgi < kStages; ++sgi)
+      if (pio < my_items) issue(sgi);
+  }
 
   double acc[SLOTS][VEC];
   int cnt[SLOTS][VEC];
@@ -757,6 +850,7 @@ __global__ void __launch_bounds__(R::kWarps * 32, 1) slab_reduce_ijk_tma_kernel(
   };
 
   uint32_t parity = 0;
+  int stage = 0;
   // consumer cursor: chunk j of item ordinal io; cls = the chunk class (j % kWarps) this warp serves in item io -
   // a rotation of the warp index, so the combine order, hence every bit of the result, does not depend on where
   // the item sits in the batch
@@ -777,23 +871,38 @@ __global__ void __launch_bounds__(R::kWarps * 32, 1) slab_reduce_ijk_tma_kernel(
     const bool do_mask = (f == SPC_QL) && g.want_mask;
     const int bytes = (int)min((long long)g.chunk_bytes, g.item_bytes - (long long)j * g.chunk_bytes);
     const int nper = bytes / (P * 16);
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait(bar0 + 8 * stage, parity)) {
     }
-    parity ^= 1;
+    const uint8_t* sbuf = wbuf + stage * kChunk;
     if (do_mask) {
-      // mask word of vector v of the item: v / LPW (nk % 32 == 0 on this path when the mask is wanted)
-      uint32_t* mw = a.mask + (size_t)c * ((size_t)a.S * (g.nk >> 5)) + ((size_t)j * (g.chunk_bytes >> 4)) / LPW + lane / LPW;
-      ijk_chunk<T, SLOTS, R::kBatch5, true, true>(wbuf, nper, lane, a.thr, mw, acc, cnt);
+      // mask word of vector v of the item: v / LPW (nk % 32 == 0 on this path when the mask is wanted); mw0 = word of the
+      // chunk's first vector (whole periods per chunk, and 32 | P, so it is a whole number of words)
+      uint32_t* mw0 = a.mask + (size_t)c * ((size_t)a.S * (g.nk >> 5)) + ((size_t)j * (g.chunk_bytes >> 4)) / LPW;
+      ijk_chunk_mask<T, SLOTS, R::kBatch5>(sbuf, nper, lane, a.thr, a.thr_f, mw0, acc, cnt);
     } else if (is_ql) {
-      ijk_chunk<T, SLOTS, R::kBatch5, true, false>(wbuf, nper, lane, a.thr, nullptr, acc, cnt);
+      ijk_chunk<T, SLOTS, R::kBatch5, true, false>(sbuf, nper, lane, a.thr, nullptr, acc, cnt);
     } else {
-      ijk_chunk<T, SLOTS, R::kBatch5, false, false>(wbuf, nper, lane, a.thr, nullptr, acc, cnt);
+      ijk_chunk<T, SLOTS, R::kBatch5, false, false>(sbuf, nper, lane, a.thr, nullptr, acc, cnt);
     }
     __syncwarp();  // every lane is done with the stage before it is refilled
-    if (lane == 0 && pio < my_items) issue();
+    if (lane == 0 && pio < my_items) issue(stage);
+    if (++stage == kStages) {
+      stage = 0;
+      parity ^= 1;
+    }
     j += kWarps;
   }
   combine(true);
+}
+
+// The float32 form of the cloud test: (double)x > thr for a float32 x is the same predicate as x >= t with
+// t = the smallest float32 strictly above thr (exact, including zeros, denormals and infinities; NaN on either side
+// compares false both ways). One FSETP per value instead of a conversion-dependent DSETP.
+float float_threshold(double thr) {
+  if (thr != thr || thr == (double)INFINITY) return NAN;     // nothing is greater than NaN / +inf
+  const float f = (float)thr;                               // round to nearest (may be +-inf)
+  if ((double)f > thr) return f;
+  return nextafterf(f, INFINITY);
 }
 
 bool fast_path(int dtype, long long S) {
@@ -910,12 +1019,16 @@ int launch_kji(spc_handle h, const K1Args& a, bool fast, cudaStream_t st) {
   return SPC_OK;
 }
 
-using IjkProd = IjkRing<12, 8192, 2>;
+// production IJK ring (round-2 sweep, profiles/README.md): 8 warps x 2 stages x 8 KB keeps a copy in flight while a warp
+// reduces the other stage - the heavier ql chunks (flags, counts, mask) no longer stall the stream: 6.57 -> 6.95 TB/s with
+// the mask, 6.90 -> 7.19 TB/s without (the 12-warp single-stage ring of round 1 is tuning variant 7)
+using IjkProd = IjkRing<8, 8192, 3, 2>;
 
 template <typename T, int SLOTS, typename R>
 constexpr size_t ijk_smem() {
   constexpr int VEC = 16 / (int)sizeof(T), P = SLOTS * 32;
-  return (size_t)R::kWarps * R::kChunk + (size_t)R::kWarps * P * VEC * (sizeof(double) + sizeof(int)) + (size_t)R::kWarps * 8 + 16;
+  return (size_t)R::kWarps * R::kStages * R::kChunk + (size_t)R::kWarps * P * VEC * (sizeof(double) + sizeof(int)) +
+         (size_t)R::kWarps * R::kStages * 8 + 16;
 }
 template <typename T, int SLOTS, typename R>
 int configure_ijk_tma() {
@@ -938,7 +1051,14 @@ int launch_ijk_tma(spc_handle h, const K1Args& a, IjkArgs g, cudaStream_t st) {
 template <typename T, int SLOTS>
 int launch_ijk_tma_variant(spc_handle h, const K1Args& a, const IjkArgs& g, cudaStream_t st) {
 #ifdef SPC_TUNING
-  if (h->ijk_variant == 2) return launch_ijk_tma<T, SLOTS, IjkRing<12, 8192, 1>>(h, a, g, st);
+  switch (h->ijk_variant) {       // (warps, chunk, periods per pass, stages)
+    case 2: return launch_ijk_tma<T, SLOTS, IjkRing<12, 8192, 1>>(h, a, g, st);
+    case 3: return launch_ijk_tma<T, SLOTS, IjkRing<8, 8192, 2, 2>>(h, a, g, st);
+    case 4: return launch_ijk_tma<T, SLOTS, IjkRing<6, 8192, 2, 3>>(h, a, g, st);
+    case 6: return launch_ijk_tma<T, SLOTS, IjkRing<10, 8192, 2, 1>>(h, a, g, st);
+    case 7: return launch_ijk_tma<T, SLOTS, IjkRing<12, 8192, 2, 1>>(h, a, g, st);
+    default: break;
+  }
 #endif
   return launch_ijk_tma<T, SLOTS, IjkProd>(h, a, g, st);
 }
@@ -1024,11 +1144,18 @@ int configure_all() {
   SPC_K1_VARIANTS2(Y)
 #undef Y
   if ((rc = configure_tma_pair<T, 16>())) return rc;
-  if ((rc = configure_ijk_tma<T, 1, IjkRing<12, 8192, 1>>())) return rc;
-  if ((rc = configure_ijk_tma<T, 2, IjkRing<12, 8192, 1>>())) return rc;
-  if ((rc = configure_ijk_tma<T, 3, IjkRing<12, 8192, 1>>())) return rc;
-  if ((rc = configure_ijk_tma<T, 4, IjkRing<12, 8192, 1>>())) return rc;
-  if ((rc = configure_ijk_tma<T, 5, IjkRing<12, 8192, 1>>())) return rc;
+#define SPC_IJK_CFG(...)                                                   \
+  if ((rc = configure_ijk_tma<T, 1, IjkRing<__VA_ARGS__>>())) return rc;   \
+  if ((rc = configure_ijk_tma<T, 2, IjkRing<__VA_ARGS__>>())) return rc;   \
+  if ((rc = configure_ijk_tma<T, 3, IjkRing<__VA_ARGS__>>())) return rc;   \
+  if ((rc = configure_ijk_tma<T, 4, IjkRing<__VA_ARGS__>>())) return rc;   \
+  if ((rc = configure_ijk_tma<T, 5, IjkRing<__VA_ARGS__>>())) return rc;
+  SPC_IJK_CFG(12, 8192, 1)
+  SPC_IJK_CFG(8, 8192, 2, 2)
+  SPC_IJK_CFG(6, 8192, 2, 3)
+  SPC_IJK_CFG(10, 8192, 2, 1)
+  SPC_IJK_CFG(12, 8192, 2, 1)
+#undef SPC_IJK_CFG
 #endif
   return rc;
 }
@@ -1086,6 +1213,7 @@ int spc_slab_reduce(spc_handle h, const void* const vol[5], int dtype, int layou
   a.cnt = cnt;
   a.mask = mask;
   a.thr = ql_thresh;
+  a.thr_f = float_threshold(ql_thresh);
   a.per_field = (long long)ncol * nk;
   a.total = a.per_field * SPC_NFIELDS;
   a.S = (int)S;
