@@ -188,20 +188,29 @@ def bind_host_thread_to_gpu(device):
 
 
 def _spin_until(read, value, timeout_s, what):
-    """Poll `read() >= value`: a short busy phase (the GPU step is tens of microseconds to milliseconds away), then
-    sleeps that back off to 0.2 ms so a long wait does not burn a core. x86-TSO / the C11 model of CPython's buffer
-    reads make a plain load sufficient for a word written with a release store by the GPU or by another process."""
-    t0 = time.perf_counter()
+    """Poll `read() >= value`. The wait is one GPU step away (tens of microseconds to a few milliseconds), and a timed
+    sleep would add its wake-up latency (50-100 us measured) to every step, so: a short pure spin, then spinning with
+    sched_yield() (returns at once when nothing else wants the core, gives it up when something does), and only after
+    50 ms - a peer that is really late - sleeps of 0.2 ms so that a long wait does not burn a core. x86-TSO makes a
+    plain load sufficient for a word written with a release store by the GPU or by another process."""
     n = 0
+    t0 = None
     while True:
         if read() >= value:
             return
         n += 1
-        if n > 2000:
-            el = time.perf_counter() - t0
-            if el > timeout_s:
-                raise RuntimeError("%s: waited %.0f s" % (what, el))
-            time.sleep(min(2e-4, 1e-6 * (n - 2000)))
+        if n <= 2000:
+            continue
+        if t0 is None:
+            t0 = time.perf_counter()
+        if n % 64:
+            os.sched_yield()
+            continue
+        el = time.perf_counter() - t0
+        if el > timeout_s:
+            raise RuntimeError("%s: waited %.0f s" % (what, el))
+        if el > 0.05:
+            time.sleep(2e-4)
 
 
 class HostExchange(object):
@@ -224,9 +233,14 @@ class HostExchange(object):
 
     HEADER_WORDS = 8     # int64: [0] step number of the inputs, [1] lev0 of their level window
 
-    def __init__(self, pipe, world, rank, owner=0, group=None, register=True, tag="x", timeout_s=60.0, window=True):
+    def __init__(self, pipe, world, rank, owner=0, group=None, register=True, tag="x", timeout_s=60.0, window=True,
+                 direct=True):
+        """direct=True: K3 stores the rank's block into the shared buffer and raises the flag itself (no host call
+        after the launch). direct=False: the rank copies its block device->host with the copy engine, synchronises its
+        stream and sets the flag from the host (faster for blocks of many MB: the copy engine moves ~54 GB/s, stores
+        issued by the SMs ~33 GB/s)."""
         self.pipe, self.world, self.rank, self.owner, self.group = pipe, world, rank, owner, group
-        self.timeout_s, self.window = timeout_s, window
+        self.timeout_s, self.window, self.direct = timeout_s, window, direct
         staging = pipe.staging
         ncol, nlev, dtype = staging.ncol, staging.nlev_max, staging.dtype
         self.ncol, self.nlev = ncol, nlev
@@ -295,7 +309,7 @@ class HostExchange(object):
         self._hdr_np, self._flags_np = self.header.numpy(), self.flags.numpy()    # plain loads for the polling loops
         self.lev0 = 0
         self.step_no = 0
-        if self.registered:      # K3 of this rank stores into the shared buffer and signals its flag there
+        if self.registered and direct:      # K3 of this rank stores into the shared buffer and signals its flag there
             pipe.bind_host_output(self.dev_base + self._off_out, self.dev_base + self._off_flags, col0=rank * ncol, slot=rank)
         torch.distributed.barrier(group=group)
 
@@ -367,11 +381,13 @@ class HostExchange(object):
         the shared buffer (`out()` is complete on the owner only); the other ranks return at once. Without a mapped
         buffer (CPU tests) every rank copies its block and sets its flag from the host."""
         pipe = self.pipe
-        if not self.registered:
+        if not (self.registered and self.direct):
             lo = self.rank * self.ncol
-            self.out()[lo:lo + self.ncol].copy_(pipe.tend)
+            self.out()[lo:lo + self.ncol].copy_(pipe.tend, non_blocking=True)
+            if pipe.tend.is_cuda:
+                torch.cuda.current_stream(pipe.tend.device).synchronize()
             pipe.epoch += 1
-            self.flags[_abi.SYNC_FLAG0 + self.rank] = pipe.epoch
+            self._flags_np[_abi.SYNC_FLAG0 + self.rank] = pipe.epoch
         if self.rank == self.owner:
             fl, want = self._flags_np, pipe.epoch
             for r in range(self.world):
