@@ -40,6 +40,7 @@ faulthandler.enable()      # a rank that dies on a signal leaves a traceback ins
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(1, os.path.join(ROOT, "tests"))      # synth_les: the synthetic LES volumes (data generation, not product)
 
 import numpy as np  # noqa: E402
 
@@ -115,11 +116,12 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------------------------ CPU legs
 def _cpu_sample_inputs(ncols, nx, ny, nk, nlev, np_dtype, seed, col0=0):
+    import synth_les
     from sp_coupler_b200 import synth
     zf, zh = synth.les_grid(nk)
     gcm = synth.make_gcm_columns(ncols, nlev, seed=seed, dtype=np_dtype, col0=col0)
     aux = synth.make_les_aux(ncols, nk, seed=seed, dtype=np_dtype, col0=col0)
-    vols = synth.make_les_volumes(gcm, zf, nx, ny, seed=seed, dtype=np_dtype, col0=col0)
+    vols = synth_les.make_les_volumes(gcm, zf, nx, ny, seed=seed, dtype=np_dtype, col0=col0)
     return zf, zh, gcm, aux, vols
 
 
@@ -275,6 +277,7 @@ def k1_traffic(config, layout, ncol):
 def run_b200(args):
     import torch
     import torch.distributed as dist
+    import synth_les
     from sp_coupler_b200 import synth
     from sp_coupler_b200.coupler import Coupler
     from sp_coupler_b200.pipeline import CouplingPipeline, HostExchange, bind_host_thread_to_gpu
@@ -356,7 +359,7 @@ def run_b200(args):
             pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, tdt, couple_surface=True, gather=gather, layout=args.layout)
         pipe.staging.fill_host(gcm_host)
         pipe.staging.upload()
-        vols = synth.device_les_volumes(cpl, gcm_host, zf, nx, ny, seed=SEED, dtype=tdt, col0=col0)
+        vols = synth_les.device_les_volumes(cpl, gcm_host, zf, nx, ny, seed=SEED, dtype=tdt, col0=col0)
         if args.layout == "ijk":     # the (itot, jtot, ktot) C-order view OMUSE hands to Python: k fastest
             for i in range(len(vols)):
                 vols[i] = vols[i].permute(0, 3, 2, 1).contiguous()
@@ -528,7 +531,7 @@ def run_b200(args):
             for r in range(world):
                 sl = slice(r * ncol, (r + 1) * ncol)
                 g = {k: v[sl] for k, v in gcm_all.items()}
-                v = synth.device_les_volumes(cpl, g, zf, nx, ny, seed=SEED, dtype=tdt, col0=r * ncol)
+                v = synth_les.device_les_volumes(cpl, g, zf, nx, ny, seed=SEED, dtype=tdt, col0=r * ncol)
                 if args.layout == "ijk":
                     v = [x.permute(0, 3, 2, 1).contiguous() for x in v]
                 sp.staging.fill_host(g)

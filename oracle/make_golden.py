@@ -14,6 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_driver  # noqa: E402
+sys.path.insert(1, os.path.join(ROOT, "tests"))
+import synth_les  # noqa: E402
 from sp_coupler_b200 import synth  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
@@ -31,7 +33,7 @@ def case_inputs(ncol, nlev, nk, seed):
     zf, zh = synth.les_grid(nk, dz)
     gcm = synth.make_gcm_columns(ncol, nlev, seed=seed)
     aux = synth.make_les_aux(ncol, nk, seed=seed)
-    plan = synth.les_volume_plan(gcm, zf)
+    plan = synth_les.les_volume_plan(gcm, zf)
     rng = np.random.default_rng(seed + 7)
     lp = {f: plan[f][0] + plan[f][1] * 0.01 * rng.normal(size=plan[f][0].shape) for f in ("THL", "QT", "U", "V")}
     lp["QL"] = np.maximum(1e-5 * rng.normal(size=(ncol, nk)) + 5e-6, 0.0)

@@ -3,6 +3,7 @@ answer, and the device upload."""
 import numpy as np
 
 from oracle import numpy_batched as nb
+import synth_les
 from sp_coupler_b200 import synth
 from sp_coupler_b200.constants import LES_FIELDS
 
@@ -12,7 +13,7 @@ def host_case(ncol, nx, ny, nk, nlev, dtype=np.float32, seed=42, layout=0, dz=No
     zf, zh = synth.les_grid(nk, dz)
     gcm = synth.make_gcm_columns(ncol, nlev, seed=seed, dtype=dtype)
     aux = synth.make_les_aux(ncol, nk, seed=seed, dtype=dtype)
-    vols = synth.make_les_volumes(gcm, zf, nx, ny, seed=seed, dtype=dtype)
+    vols = synth_les.make_les_volumes(gcm, zf, nx, ny, seed=seed, dtype=dtype)
     if layout == 1:
         vols = {f: np.ascontiguousarray(np.transpose(v, (0, 3, 2, 1))) for f, v in vols.items()}
     return dict(zf=zf, zh=zh, gcm=gcm, aux=aux, vols=vols, ncol=ncol, nx=nx, ny=ny, nk=nk, nlev=nlev,

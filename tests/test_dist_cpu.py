@@ -11,6 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import numpy_batched as nb
+import synth_les
 from sp_coupler_b200 import synth
 from sp_coupler_b200.constants import TENDENCIES
 from sp_coupler_b200.pipeline import gather_tendencies, shard_columns
@@ -22,7 +23,7 @@ def _tendencies(col0, ncol):
     zf, zh = synth.les_grid(NK, 200.0)
     gcm = synth.make_gcm_columns(ncol, NLEV, seed=5, col0=col0, ncol_total=NCOL)
     aux = synth.make_les_aux(ncol, NK, seed=5, col0=col0, ncol_total=NCOL)
-    vols = synth.make_les_volumes(gcm, zf, NX, NX, seed=5, dtype=np.float32, col0=col0)
+    vols = synth_les.make_les_volumes(gcm, zf, NX, NX, seed=5, dtype=np.float32, col0=col0)
     r = nb.coupling_step(gcm, zf, zh, vols, aux, aux["PS"], 900.0, 1.0, 1.0, True)
     return np.stack([r["tendencies"][k] for k in TENDENCIES], axis=1), vols
 
@@ -117,7 +118,7 @@ class _OraclePipe(object):
         gcm = {k: v.numpy() for k, v in self.staging.dev.items()}
         aux = synth.make_les_aux(self.ncol, NK, seed=5, col0=self.col0, ncol_total=NCOL)
         ref = synth.make_gcm_columns(self.ncol, NLEV, seed=5, col0=self.col0, ncol_total=NCOL)
-        vols = synth.make_les_volumes(ref, zf, NX, NX, seed=5, dtype=np.float32, col0=self.col0)
+        vols = synth_les.make_les_volumes(ref, zf, NX, NX, seed=5, dtype=np.float32, col0=self.col0)
         r = nb.coupling_step(gcm, zf, zh, vols, aux, aux["PS"], dt, f_les, f_gcm, True)
         self.tend.copy_(torch.from_numpy(np.stack([r["tendencies"][k] for k in TENDENCIES], axis=1)))
         return r["forcings"]
@@ -161,7 +162,7 @@ def test_host_exchange_shared_buffer(tmp_path, window):
     zf, zh = synth.les_grid(NK, 200.0)
     full = synth.make_gcm_columns(NCOL, NLEV, seed=5)
     aux = synth.make_les_aux(NCOL, NK, seed=5)
-    vols = synth.make_les_volumes(full, zf, NX, NX, seed=5, dtype=np.float32)
+    vols = synth_les.make_les_volumes(full, zf, NX, NX, seed=5, dtype=np.float32)
     for it in range(2):
         g = dict(full)
         if it == 1:

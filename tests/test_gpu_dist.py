@@ -29,6 +29,7 @@ def _worker(rank, world, port, outdir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     msgs = []
     try:
+        import synth_les
         from sp_coupler_b200 import synth
         from sp_coupler_b200.coupler import Coupler
         from sp_coupler_b200.pipeline import CouplingPipeline, HostExchange
@@ -40,7 +41,7 @@ def _worker(rank, world, port, outdir):
         def inputs(col0, ncol):
             gcm = synth.make_gcm_columns(ncol, NLEV, seed=11, dtype=np.float32, col0=col0, ncol_total=ntot)
             aux = up(synth.make_les_aux(ncol, NK, seed=11, dtype=np.float32, col0=col0, ncol_total=ntot))
-            vols = synth.device_les_volumes(cpl, gcm, zf, NX, NX, seed=11, col0=col0)
+            vols = synth_les.device_les_volumes(cpl, gcm, zf, NX, NX, seed=11, col0=col0)
             return gcm, aux, vols
 
         def run(pipe, vols, aux, gcm, graph, sync_each=True):
@@ -160,6 +161,7 @@ def _c5_worker(rank, world, port, outdir):
     msgs = []
     try:
         from oracle import numpy_batched as nb
+        import synth_les
         from sp_coupler_b200 import synth
         from sp_coupler_b200.constants import TENDENCIES
         from sp_coupler_b200.coupler import Coupler
@@ -175,7 +177,7 @@ def _c5_worker(rank, world, port, outdir):
             pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, torch.float32, gather=gather)
             pipe.staging.fill_host(gcm)
             pipe.staging.upload()
-            pipe.attach_les(synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=46, col0=r * ncol),
+            pipe.attach_les(synth_les.device_les_volumes(cpl, gcm, zf, nx, nx, seed=46, col0=r * ncol),
                             {k: torch.from_numpy(v).to(dev) for k, v in aux.items()})
             pipe.les_profiles()
             return pipe, gcm, aux
@@ -192,7 +194,7 @@ def _c5_worker(rank, world, port, outdir):
         c = (37 * (rank + 1)) % ncol
         g1 = {k: v[c:c + 1] for k, v in gcm.items()}
         a1 = {k: v[c:c + 1] for k, v in aux.items()}
-        hv = synth.make_les_volumes(g1, zf, nx, nx, seed=46, dtype=np.float32, col0=rank * ncol + c)
+        hv = synth_les.make_les_volumes(g1, zf, nx, nx, seed=46, dtype=np.float32, col0=rank * ncol + c)
         ref = nb.coupling_step(g1, zf, zh, hv, a1, a1["PS"], 900.0, 1.0, 1.0, True)
         got = pipe.tend[c].cpu().numpy()
         for i, k in enumerate(TENDENCIES):

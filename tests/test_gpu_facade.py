@@ -1,6 +1,8 @@
 """The host-side mirror of the reference interface (sp_coupler_b200/{spcpl,sputils,splib,spdummy}.py):
 per-LES reference-shaped calls and the batched route must give the same numbers as the oracle."""
 import numpy as np
+
+import synth_les
 import pytest
 
 from conftest import relerr
@@ -118,7 +120,7 @@ def test_set_les_state_and_diagnostics_store(world, cuda_device):
     spcpl.set_les_state(les, u, v, thl, qt, ps)
     b = splib.les_batch
     vol = n(b.vols[LES_FIELDS.index("THL")][les.i])
-    host = synth.les_state_volume(n(thl)[None, :], 0.1, synth.STREAM["THL"], b.nx, b.ny, seed=b.seed, col0=les.i,
+    host = synth_les.les_state_volume(n(thl)[None, :], 0.1, synth.STREAM["THL"], b.nx, b.ny, seed=b.seed, col0=les.i,
                                   dtype=np.float64)[0]
     assert np.array_equal(vol, host)
     assert abs(vol.mean(axis=(1, 2)) - n(thl)).max() < 0.1 * 4 / np.sqrt(256)      # uniform noise, amplitude 0.1 K

@@ -8,6 +8,7 @@ import torch
 
 from conftest import relerr
 from oracle import numpy_batched as nb
+import synth_les
 from sp_coupler_b200 import synth
 from sp_coupler_b200.constants import LES_FIELDS, TENDENCIES
 
@@ -36,7 +37,7 @@ def _run_config(cpl, dev, ncol, nx, nk, nlev, spots, chunk):
     zf, zh = synth.les_grid(nk)
     gcm = synth.make_gcm_columns(ncol, nlev, seed=44, dtype=np.float32)
     aux = synth.make_les_aux(ncol, nk, seed=44, dtype=np.float32)
-    vols = synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=44, dtype=torch.float32)
+    vols = synth_les.device_les_volumes(cpl, gcm, zf, nx, nx, seed=44, dtype=torch.float32)
     S = nx * nx
     slab = cpl.slab_reduce(vols)
     # (1) independent float64 reduction + exact counts over ALL columns, chunked to bound memory
@@ -65,7 +66,7 @@ def _run_config(cpl, dev, ncol, nx, nk, nlev, spots, chunk):
     for c in spots:
         g1 = {k: v[c:c + 1] for k, v in gcm.items()}
         a1 = {k: v[c:c + 1] for k, v in aux.items()}
-        hv = synth.make_les_volumes(g1, zf, nx, nx, seed=44, dtype=np.float32, col0=c)
+        hv = synth_les.make_les_volumes(g1, zf, nx, nx, seed=44, dtype=np.float32, col0=c)
         for f, name in enumerate(LES_FIELDS):                      # device generator == host generator
             assert np.array_equal(n(vols[f][c]), hv[name][0]), name
         ref = nb.coupling_step(g1, zf, zh, hv, a1, a1["PS"], 900.0, 1.0, 1.0, True)
@@ -102,11 +103,11 @@ def test_c2_full_size_every_column_fp64(cpl, cuda_device):
     zf, zh = synth.les_grid(nk)
     gcm = synth.make_gcm_columns(ncol, nlev, seed=43, dtype=np.float64)
     aux = synth.make_les_aux(ncol, nk, seed=43, dtype=np.float64)
-    hv = synth.make_les_volumes(gcm, zf, nx, nx, seed=43, dtype=np.float64)
+    hv = synth_les.make_les_volumes(gcm, zf, nx, nx, seed=43, dtype=np.float64)
     ref = nb.coupling_step(gcm, zf, zh, hv, aux, aux["PS"], 900.0, 1.0, 1.0, True)
     dev = cuda_device
     vols = [torch.from_numpy(hv[f]).to(dev) for f in LES_FIELDS]
-    gen = synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=43, dtype=torch.float64)
+    gen = synth_les.device_les_volumes(cpl, gcm, zf, nx, nx, seed=43, dtype=torch.float64)
     for a, b, f in zip(vols, gen, LES_FIELDS):                     # device generator == host generator, all columns
         assert torch.equal(a, b), f
     del gen
@@ -156,7 +157,7 @@ def test_ijk_layout_full_columns(cpl, cuda_device):
     ncol, nx, nk, nlev = 512, 64, 160, 91
     zf, zh = synth.les_grid(nk)
     gcm = synth.make_gcm_columns(ncol, nlev, seed=45, dtype=np.float32)
-    vols = synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=45, dtype=torch.float32)
+    vols = synth_les.device_les_volumes(cpl, gcm, zf, nx, nx, seed=45, dtype=torch.float32)
     kji = cpl.slab_reduce(vols)
     ijk_vols = [v.permute(0, 3, 2, 1).contiguous() for v in vols]
     del vols

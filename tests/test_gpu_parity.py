@@ -259,6 +259,7 @@ def test_cloud_fraction_index_mapping_kat(cpl, cuda_device):
 
 def test_set_les_state_bit_identical_to_host_generator(cpl, cuda_device):
     import torch
+    import synth_les
     from sp_coupler_b200 import synth
     rng = np.random.default_rng(2)
     for dtype, td in ((np.float32, torch.float32), (np.float64, torch.float64)):
@@ -267,9 +268,9 @@ def test_set_les_state_bit_identical_to_host_generator(cpl, cuda_device):
             sub = prof + 0.05 * rng.normal(size=(ncol, nk))
             t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
             v = n(cpl.set_les_state(t(prof), 0.1, 3, nx, ny, seed=42, col0=5, dtype=td))
-            assert np.array_equal(v, synth.les_state_volume(prof, 0.1, 3, nx, ny, seed=42, col0=5, dtype=dtype))
+            assert np.array_equal(v, synth_les.les_state_volume(prof, 0.1, 3, nx, ny, seed=42, col0=5, dtype=dtype))
             v = n(cpl.set_les_state(t(prof), 0.1, 1, nx, ny, seed=7, col0=0, sub=t(sub), clamp0=True, dtype=td))
-            h = synth.les_state_volume(prof, 0.1, 1, nx, ny, seed=7, col0=0, sub=sub, clamp0=True, dtype=dtype)
+            h = synth_les.les_state_volume(prof, 0.1, 1, nx, ny, seed=7, col0=0, sub=sub, clamp0=True, dtype=dtype)
             assert np.array_equal(v, h) and (v == 0).any() and (v > 0).any()
             # every SUB / CLAMP instantiation, the reference amplitudes (spcpl.py:285-291), no noise, and an
             # amplitude too close to the subnormals for the slab kernel's exact-scaling form (generic kernel)
@@ -278,7 +279,7 @@ def test_set_les_state_bit_identical_to_host_generator(cpl, cuda_device):
                     kw = dict(seed=11, col0=2, clamp0=clamp)
                     v = n(cpl.set_les_state(t(prof - 300.0), amp, 2, nx, ny, sub=t(sub - 300.0) if use_sub else None,
                                             dtype=td, **kw))
-                    h = synth.les_state_volume(prof - 300.0, amp, 2, nx, ny, sub=(sub - 300.0) if use_sub else None,
+                    h = synth_les.les_state_volume(prof - 300.0, amp, 2, nx, ny, sub=(sub - 300.0) if use_sub else None,
                                                dtype=dtype, **kw)
                     assert np.array_equal(v, h), (amp, use_sub, clamp)
 
@@ -381,6 +382,7 @@ def test_cuda_graph_step_is_bit_identical(cpl, cuda_device, ncol):
     """CouplingPipeline.capture(): the replayed graph (K2 -> K1 -> K3 with its fused projection) gives the bits of the
     eager step, also after the inputs changed in place (new GCM profiles uploaded, LES volumes rewritten)."""
     import torch
+    import synth_les
     from sp_coupler_b200 import synth
     from sp_coupler_b200.pipeline import CouplingPipeline
     nx, nk, nlev = 16, 160, 91
@@ -392,7 +394,7 @@ def test_cuda_graph_step_is_bit_identical(cpl, cuda_device, ncol):
         p = CouplingPipeline(cpl, zf, zh, ncol, nlev, torch.float32)
         p.staging.fill_host(gcm)
         p.staging.upload()
-        p.attach_les(synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=3), aux)
+        p.attach_les(synth_les.device_les_volumes(cpl, gcm, zf, nx, nx, seed=3), aux)
         p.les_profiles()
         pipes.append(p)
     eager, graphed = pipes
@@ -422,13 +424,14 @@ def test_level_window_host_step(cpl, cuda_device, nlev, graph):
     bit), everything above lev0 is zero in the full result, the forcings are identical, and the host-side bound is
     one level looser than the kernel's start_index."""
     import torch
+    import synth_les
     from sp_coupler_b200 import synth
     from sp_coupler_b200.pipeline import CouplingPipeline
     ncol, nx, nk = 12, 16, 160
     zf, zh = synth.les_grid(nk)
     gcm = synth.make_gcm_columns(ncol, nlev, seed=21, dtype=np.float32)
     aux = {k: torch.from_numpy(v).to(cuda_device) for k, v in synth.make_les_aux(ncol, nk, seed=21, dtype=np.float32).items()}
-    vols = synth.device_les_volumes(cpl, gcm, zf, nx, nx, seed=21)
+    vols = synth_les.device_les_volumes(cpl, gcm, zf, nx, nx, seed=21)
     full_pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, torch.float32)
     full_pipe.staging.fill_host(gcm)
     full_pipe.staging.upload()

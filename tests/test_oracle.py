@@ -148,12 +148,13 @@ def test_slab_oracle_small():
 def test_oracle_matches_reference_live(nlev, nk, seed, dt, f_les, f_gcm, cons):
     """The restatement against the UNMODIFIED reference run here (oracle/ref_driver.py), beyond the committed golden
     cases: other seeds (orography, surface pressure, fluxes), level sets, factors, and the conservative option."""
+    import synth_les
     from sp_coupler_b200 import synth
     ncol = 3
     zf, zh = synth.les_grid(nk, 25.0 if nk == 160 else 200.0)
     g = synth.make_gcm_columns(ncol, nlev, seed=seed)
     aux = synth.make_les_aux(ncol, nk, seed=seed)
-    plan = synth.les_volume_plan(g, zf)
+    plan = synth_les.les_volume_plan(g, zf)
     rng = np.random.default_rng(seed)
     lp = {f: plan[f][0] + plan[f][1] * 0.02 * rng.normal(size=plan[f][0].shape) for f in ("THL", "QT", "U", "V")}
     lp["QL"] = np.maximum(4e-6 + 3e-6 * rng.normal(size=(ncol, nk)), 0.0)

@@ -11,6 +11,8 @@ os.environ.setdefault("SPCPL_B200_LIB", os.path.join(ROOT, "sp_coupler_b200", "l
 import numpy as np
 import torch
 
+sys.path.insert(1, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import synth_les
 from sp_coupler_b200 import synth
 from sp_coupler_b200.coupler import Coupler
 
@@ -34,7 +36,7 @@ td = torch.float32 if a.dtype == "f32" else torch.float64
 zf, zh = synth.les_grid(a.nk)
 gcm = synth.make_gcm_columns(a.ncol, 91)
 t0 = time.time()
-vols = synth.device_les_volumes(cpl, gcm, zf, a.nx, a.nx, dtype=td)
+vols = synth_les.device_les_volumes(cpl, gcm, zf, a.nx, a.nx, dtype=td)
 torch.cuda.synchronize()
 print("generated %.2f GB in %.2fs" % (sum(v.numel() * v.element_size() for v in vols) / 1e9, time.time() - t0))
 if a.layout == "ijk":

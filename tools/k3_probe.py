@@ -6,6 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
+sys.path.insert(1, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import synth_les
 from sp_coupler_b200 import synth
 from sp_coupler_b200.coupler import Coupler
 from sp_coupler_b200.pipeline import CouplingPipeline
@@ -19,7 +21,7 @@ aux = synth.make_les_aux(ncol, 160, dtype=np.float32)
 pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, torch.float32)
 pipe.staging.fill_host(gcm)
 pipe.staging.upload()
-pipe.attach_les(synth.device_les_volumes(cpl, gcm, zf, nx, nx), {k: torch.from_numpy(v).to(dev) for k, v in aux.items()})
+pipe.attach_les(synth_les.device_les_volumes(cpl, gcm, zf, nx, nx), {k: torch.from_numpy(v).to(dev) for k, v in aux.items()})
 slab = pipe.les_profiles()
 frc = pipe.forcings(900.0, 1.0)
 torch.cuda.synchronize()

@@ -13,6 +13,8 @@ import numpy as np
 import torch
 
 from bench import CONFIGS
+sys.path.insert(1, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import synth_les
 from sp_coupler_b200 import synth
 from sp_coupler_b200.coupler import Coupler
 from sp_coupler_b200.pipeline import CouplingPipeline
@@ -30,7 +32,7 @@ cpl = Coupler(dev)
 zf, zh = synth.les_grid(nk)
 gcm = synth.make_gcm_columns(ncol, nlev, seed=44, dtype=ndt)
 aux = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_les_aux(ncol, nk, seed=44, dtype=ndt).items()}
-vols = synth.device_les_volumes(cpl, gcm, zf, nx, ny, seed=44, dtype=tdt)
+vols = synth_les.device_les_volumes(cpl, gcm, zf, nx, ny, seed=44, dtype=tdt)
 if layout == "ijk":
     vols = [v.permute(0, 3, 2, 1).contiguous() for v in vols]
 pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, tdt, couple_surface=True, gather=False, layout=layout)

@@ -9,6 +9,8 @@ if len(sys.argv) > 4:   # the thread sweep needs spc_tune_profiles: only in the 
 import numpy as np
 import torch
 
+sys.path.insert(1, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import synth_les
 from sp_coupler_b200 import synth
 from sp_coupler_b200.coupler import Coupler
 from sp_coupler_b200.pipeline import CouplingPipeline
@@ -24,7 +26,7 @@ aux = synth.make_les_aux(ncol, 160, dtype=np.float32)
 pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, torch.float32)
 pipe.staging.fill_host(gcm)
 pipe.staging.upload()
-pipe.attach_les(synth.device_les_volumes(cpl, gcm, zf, nx, nx), {k: torch.from_numpy(v).to(dev) for k, v in aux.items()})
+pipe.attach_les(synth_les.device_les_volumes(cpl, gcm, zf, nx, nx), {k: torch.from_numpy(v).to(dev) for k, v in aux.items()})
 pipe.les_profiles()
 torch.cuda.synchronize()
 
