@@ -357,7 +357,15 @@ def run_b200(args):
                 gather, pipe = "nccl", None
         if pipe is None:
             pipe = CouplingPipeline(cpl, zf, zh, ncol, nlev, tdt, couple_surface=True, gather=gather, layout=args.layout)
-        pipe.staging.fill_host(gcm_host)
+        # the live level window of the job (pipeline.py, "Level window"): the GCM levels above the first one over the LES top
+        # carry zero tendencies and are not needed for the forcings, so the resident GCM columns are cut there; when the
+        # columns are sharded every rank runs the job-wide window (the gathered block is [ncol_total][7][nlw])
+        lev0 = pipe.first_live_level(gcm_host) if args.window else 0
+        if world > 1:
+            lv = torch.tensor([lev0], device=dev)
+            dist.all_reduce(lv, op=dist.ReduceOp.MIN)
+            lev0 = int(lv.item())
+        pipe.stage_host(gcm_host, lev0=lev0)
         pipe.staging.upload()
         vols = synth_les.device_les_volumes(cpl, gcm_host, zf, nx, ny, seed=SEED, dtype=tdt, col0=col0)
         if args.layout == "ijk":     # the (itot, jtot, ktot) C-order view OMUSE hands to Python: k fastest
@@ -368,7 +376,7 @@ def run_b200(args):
         pipe.les_profiles()                      # first-step slab means (spcpl.py:302-308)
         torch.cuda.synchronize()
         return dict(ncol=ncol, ncol_total=ncol_total, col0=col0, gcm_host=gcm_host, aux_host=aux_host, gather=gather,
-                    pipe=pipe, vols=vols, aux=aux)
+                    pipe=pipe, vols=vols, aux=aux, lev0=lev0)
 
     def capture(pipe):
         """All ranks capture together or nobody does."""
@@ -446,7 +454,7 @@ def run_b200(args):
                      "a flag the owner polls; ") +
                     "no device gather; bytes are totals over ranks; LES volumes are device-resident LES state")
         if rank == 0:
-            e2e_ok = bool(torch.equal(exch.out(), value_tend[:, :, lev0:].cpu()))
+            e2e_ok = bool(lev0 >= job["lev0"] and torch.equal(exch.out(), value_tend[:, :, lev0 - job["lev0"]:].cpu()))
     else:
         lev0 = hp.stage_host(job["gcm_host"], window=args.window)
         if args.direct:
@@ -460,7 +468,7 @@ def run_b200(args):
                     ("K3 stores the tendencies into pinned host memory and raises a flag the host polls; " if args.direct else
                      "tendencies D2H into pinned host memory (one copy), stream synchronised; ") +
                     "LES volumes are device-resident LES state")
-        e2e_ok = bool(torch.equal(hp.tend_host, value_tend[:, :, lev0:].cpu()))
+        e2e_ok = bool(lev0 >= job["lev0"] and torch.equal(hp.tend_host, value_tend[:, :, lev0 - job["lev0"]:].cpu()))
     e2e_note += "; GCM levels %d..%d of %d travel (the window up to the first level above the LES top; tendencies above are zero)" % (
         lev0, nlev - 1, nlev) if lev0 else "; all %d GCM levels travel" % nlev
     # for the record (1 GPU): the round-1 form of the leg - all levels both ways, D2H copy + stream synchronise
@@ -534,7 +542,7 @@ def run_b200(args):
                 v = synth_les.device_les_volumes(cpl, g, zf, nx, ny, seed=SEED, dtype=tdt, col0=r * ncol)
                 if args.layout == "ijk":
                     v = [x.permute(0, 3, 2, 1).contiguous() for x in v]
-                sp.staging.fill_host(g)
+                sp.stage_host(g, lev0=job["lev0"])
                 sp.staging.upload()
                 sp.attach_les(v, {k: torch.from_numpy(np.ascontiguousarray(a[sl])).to(dev) for k, a in aux_all.items()})
                 sp.slab = None
@@ -571,6 +579,8 @@ def run_b200(args):
                    "ncol_per_gpu": ncol, "storage_dtype": dts, "arithmetic": "f64", "layout": args.layout,
                    "l2": "inputs larger than L2 (%.1f GB of LES volumes per GPU streamed once per step; no reuse between steps)" % (bpc * ncol / 1e9),
                    "parallelism": par,
+                   "gcm_levels": "%d..%d of %d resident (live level window; tendencies above are zero)" % (job["lev0"], nlev - 1, nlev)
+                                 if job["lev0"] else "all %d" % nlev,
                    "step": "K2 gcm_to_les -> K1 slab_reduce -> K3 les_to_gcm (cloud projection, tendencies, delivery)",
                    "launch": "one CUDA graph replay per step" if graphed else "eager: three C-ABI calls per step"},
         "roofline": {"kernel": "slab_reduce_tma_kernel" if args.layout == "kji" else "slab_reduce_ijk_tma_kernel", "bound": "hbm",

@@ -625,10 +625,13 @@ class CouplingPipeline(object):
         h = self.staging.host if gcm_host is None else gcm_host
         return first_live_level(h["Zgfull"], torch.as_tensor(np.asarray(h["Zghalf"]))[:, -1], self._zf_top)
 
-    def stage_host(self, gcm_host, window=True):
+    def stage_host(self, gcm_host, window=True, lev0=None):
         """The host GCM's part of gather_gcm_data: pick the level window of these columns, pack them (cut to the
-        window) into the pinned staging buffer. Returns lev0. Not per step unless the GCM state changed."""
-        lev0 = self.first_live_level(gcm_host) if window else 0
+        window) into the pinned staging buffer. Returns lev0. Not per step unless the GCM state changed.
+        When the columns are sharded every rank must run the same window (the gathered block is [..][7][nlw] on the
+        owner): pass the job-wide lev0 = min over ranks of first_live_level()."""
+        if lev0 is None:
+            lev0 = self.first_live_level(gcm_host) if window else 0
         nlw = self.nlev - lev0
         if nlw != self.nlw:
             self.set_levels(nlw)

@@ -44,12 +44,12 @@ def _worker(rank, world, port, outdir):
             vols = synth_les.device_les_volumes(cpl, gcm, zf, NX, NX, seed=11, col0=col0)
             return gcm, aux, vols
 
-        def run(pipe, vols, aux, gcm, graph, sync_each=True):
+        def run(pipe, vols, aux, gcm, graph, sync_each=True, lev0=0):
             """STEPS steps; the LES state changes between steps so that a stale gather buffer would show. Without
             sync_each the steps are queued back to back (ranks may run a step ahead of each other: the alternating
             gather buffers and the in-kernel barrier must keep them apart) and only the last block is returned."""
             vols = [v.clone() for v in vols]
-            pipe.staging.fill_host(gcm)
+            pipe.stage_host(gcm, lev0=lev0)
             pipe.staging.upload()
             pipe.attach_les(vols, aux)
             pipe.les_profiles()
@@ -71,17 +71,23 @@ def _worker(rank, world, port, outdir):
         ref = run(CouplingPipeline(cpl, zf, zh, ntot, NLEV, torch.float32, gather=False), vols_all, aux_all, gcm_all, False)
         assert not torch.equal(ref[0], ref[-1])
         gcm, aux, vols = inputs(rank * NCOL, NCOL)
-        for mode, graph, sync_each in (("p2p-owner", False, True), ("p2p-owner", True, True), ("p2p-owner", False, False),
-                                       ("p2p-owner", True, False), ("p2p", False, True), ("p2p", True, False),
-                                       ("nccl", False, True)):
+        # the job-wide live level window (every rank must run the same one: the gathered block is [..][7][nlw])
+        from sp_coupler_b200.pipeline import first_live_level
+        lev_all = first_live_level(gcm_all["Zgfull"], gcm_all["Zghalf"][:, -1], float(zf[-1]))
+        if lev_all <= 0:
+            msgs.append("no level window in this case (lev0=%d)" % lev_all)
+        for mode, graph, sync_each, lev0 in (("p2p-owner", False, True, 0), ("p2p-owner", True, True, 0), ("p2p-owner", False, False, 0),
+                                             ("p2p-owner", True, False, 0), ("p2p", False, True, 0), ("p2p", True, False, 0),
+                                             ("nccl", False, True, 0), ("p2p-owner", True, True, lev_all), ("p2p", False, False, lev_all),
+                                             ("nccl", False, True, lev_all)):
             pipe = CouplingPipeline(cpl, zf, zh, NCOL, NLEV, torch.float32, gather=mode)
-            outs = run(pipe, vols, aux, gcm, graph, sync_each)
-            want = ref if sync_each else ref[-1:]
+            outs = run(pipe, vols, aux, gcm, graph, sync_each, lev0)
+            want = [r[:, :, lev0:] for r in (ref if sync_each else ref[-1:])]
             if rank == 0 or mode != "p2p-owner":
                 for it, (a, b) in enumerate(zip(outs, want)):
                     if not torch.equal(a, b):
-                        msgs.append("%s graph=%s sync_each=%s step %d: gathered block differs from the single-GPU result"
-                                    % (mode, graph, sync_each, it))
+                        msgs.append("%s graph=%s sync_each=%s lev0=%d step %d: gathered block differs from the single-GPU result"
+                                    % (mode, graph, sync_each, lev0, it))
             if pipe.sync_error():
                 msgs.append("%s graph=%s: sync error %d" % (mode, graph, pipe.sync_error()))
             del pipe
