@@ -112,3 +112,44 @@ def test_nudge_facade(cuda_device):
         o = nudge.variability_nudge(les, 900.0, False, write=False, R=R[les.i:les.i + 1])
         assert torch.equal(o["beta"][0], out_all["beta"][les.i])
     assert torch.equal(b.vols[1], qt_all)
+
+
+def test_driver_routes_agree_with_variance_forcing(cuda_device):
+    """--qt_forcing variance through the driver loop: the batched route (one nudge launch for all columns, run inside
+    set_les_forcings_all exactly where the reference runs it per LES, spcpl.py:377-382) and the per-column route
+    change the LES state, and leave it in the same state. The additive branch draws a random field per call, so the
+    comparison uses a configuration in which no level takes it (status bit 4 clear)."""
+    from sp_coupler_b200 import splib
+    states = {}
+    for per_column in (False, True):
+        splib.initialize(dict(max_num_les=3, les_nx=16, les_ny=16, les_nk=160, gcm_nlev=19, dtype="f64", cplsurf=True,
+                              per_column=per_column, write_diagnostics=False, qt_forcing="variance",
+                              variability_nudge_constant_T=False, les_spinup=0), device=cuda_device)
+        b = splib.les_batch
+        qt_start = b.vols[1].clone()
+        splib.step()                      # LES clock still 0 when the forcings are set: no nudge yet (spcpl.py:378)
+        after_first = b.vols[1].clone()
+        splib.step()                      # now the nudge runs
+        states[per_column] = (qt_start, after_first, b.vols[1].clone(), getattr(b, "last_nudge", None))
+        splib.finalize()
+    (s0, a0, f0, nudge0), (s1, a1, f1, _) = states[False], states[True]
+    assert torch.equal(s0, s1) and torch.equal(a0, a1)
+    assert nudge0 is not None and (n(nudge0["status"]) & 3).any()       # multiplicative / unsaturated nudges happened
+    if not (n(nudge0["status"]) & 4).any():
+        assert torch.equal(f0, f1)
+    # and the same run without the option leaves a different state: the option is not silently ignored
+    splib.initialize(dict(max_num_les=3, les_nx=16, les_ny=16, les_nk=160, gcm_nlev=19, dtype="f64", cplsurf=True,
+                          per_column=False, write_diagnostics=False, qt_forcing="sp", les_spinup=0), device=cuda_device)
+    splib.step()
+    splib.step()
+    assert not torch.equal(splib.les_batch.vols[1], f0)
+    splib.finalize()
+
+
+def test_unknown_qt_forcing_is_rejected(cuda_device):
+    from sp_coupler_b200 import splib, spcpl
+    splib.initialize(dict(max_num_les=2, les_nx=16, les_ny=16, les_nk=160, gcm_nlev=19, dtype="f32", cplsurf=True,
+                          per_column=False, write_diagnostics=False, qt_forcing="sp"), device=cuda_device)
+    with pytest.raises(ValueError):
+        spcpl.set_les_forcings_all(splib.les_batch, 900.0, 1.0, True, False, qt_forcing="variances")
+    splib.finalize()

@@ -39,3 +39,40 @@ def test_torch_ops_errors_are_loud(cuda_device):
     vols = [torch.zeros((1, 4, 8, 8), device=cuda_device) for _ in range(4)]
     with pytest.raises(RuntimeError):
         ops.slab_reduce(vols, 0, 0.0, torch.zeros((5, 1, 4), dtype=torch.float64, device=cuda_device), None, None)
+
+
+def test_torch_ops_reject_buffers_of_the_wrong_type_or_size(cuda_device):
+    """The registered ops forward raw pointers to the C ABI, so every caller-supplied output is checked first: a
+    float32 tendency block for float64 GCM columns, a short cloud mask or a short count buffer must raise instead of
+    letting a kernel write out of bounds."""
+    import torch
+    from sp_coupler_b200 import torch_ops
+    ops = torch_ops.load()
+    dev = cuda_device
+    ncol, nk, ny, nx, nlev = 2, 8, 8, 8, 5
+    vols = [torch.zeros((ncol, nk, ny, nx), device=dev) for _ in range(5)]
+    prof = torch.zeros((5, ncol, nk), dtype=torch.float64, device=dev)
+    mw = ops.mask_words_per_column(0, 0, nx, ny, nk)
+    good_cnt = torch.zeros((ncol, nk), dtype=torch.int32, device=dev)
+    good_mask = torch.zeros((ncol, mw), dtype=torch.int32, device=dev)
+    ops.slab_reduce(vols, 0, 0.0, prof, good_cnt, good_mask)
+    with pytest.raises(RuntimeError):
+        ops.slab_reduce(vols, 0, 0.0, prof, good_cnt, good_mask[:, :-1].contiguous())          # short mask
+    with pytest.raises(RuntimeError):
+        ops.slab_reduce(vols, 0, 0.0, prof, good_cnt[:1].contiguous(), good_mask)              # short counts
+    with pytest.raises(RuntimeError):
+        ops.slab_reduce(vols, 0, 0.0, prof, good_cnt.float(), good_mask)                       # wrong dtype
+    g = {k: torch.ones((ncol, nlev), dtype=torch.float64, device=dev) for k in ("U", "V", "T", "SH", "QL", "QI", "Pfull", "A", "Zgfull")}
+    g.update({k: torch.ones((ncol, nlev + 1), dtype=torch.float64, device=dev) for k in ("Phalf", "Zghalf")})
+    zf = torch.linspace(10.0, 80.0, nk, dtype=torch.float64, device=dev)
+    les = {"prof": prof, "QL_ice": torch.zeros((ncol, nk), dtype=torch.float64, device=dev),
+           "T": torch.zeros((ncol, nk), dtype=torch.float64, device=dev), "A": torch.zeros((ncol, nlev), dtype=torch.float64, device=dev)}
+    ok = {"tend": torch.zeros((ncol, 7, nlev), dtype=torch.float64, device=dev)}
+    ops.les_to_gcm(g, zf, None, les, nx, ny, 0, 0, 900.0, 1.0, False, ok)
+    with pytest.raises(RuntimeError):      # float32 block for float64 columns: half the bytes the kernel would write
+        ops.les_to_gcm(g, zf, None, les, nx, ny, 0, 0, 900.0, 1.0, False, {"tend": ok["tend"].float()})
+    with pytest.raises(RuntimeError):
+        ops.les_to_gcm(g, zf, None, les, nx, ny, 0, 0, 900.0, 1.0, False, {"tend": ok["tend"][:, :6].contiguous()})
+    with pytest.raises(RuntimeError):
+        ops.gcm_to_les(g, zf, None, None, None, 900.0, 1.0, False, {"ql_ref": torch.zeros((ncol, nk), device=dev)})   # float32
+    torch.cuda.synchronize()
