@@ -248,3 +248,38 @@ def test_c5_sharded_over_8_gpus(tmp_path):
     mp.spawn(_c5_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for rank in range(world):
         assert open(str(tmp_path / ("rank%d.txt" % rank))).read() == "ok", rank
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_sharded_driver_equals_single_gpu(tmp_path):
+    """spmaster.py (the reference's driver loop, splib.step) under torch.distributed.run on 2 GPUs: after 3 coupled steps
+    the GCM state of the SP columns equals the single-GPU run bit for bit, with every gather mode - NCCL all_gather,
+    fused NVLink stores (to every rank / to the owner), and the shared pinned host buffer with the level window."""
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs on the box")
+    common = ["--steps", "3", "--numles", "16", "--nx", "16", "--ny", "16", "--cplsurf"]
+    one = str(tmp_path / "one.npz")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "spmaster.py")] + common + ["--save_state", one],
+                       capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr[-2000:]
+    ref = np.load(one)
+    for mode in ("nccl", "p2p", "p2p-owner", "host"):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        out = str(tmp_path / ("two_%s.npz" % mode))
+        p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "spmaster.py")] +
+                           common + ["--gather", mode, "--save_state", out], capture_output=True, text=True, timeout=400,
+                           cwd=str(tmp_path))
+        assert p.returncode == 0, (mode, p.stderr[-3000:])
+        got = np.load(out)
+        for k in ref.files:
+            assert np.array_equal(got[k], ref[k]), (mode, k)
+    assert float(np.abs(ref["T"]).sum()) > 0
