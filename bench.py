@@ -224,10 +224,10 @@ def run_reference(args):
     return 0
 
 
-def cpu_baseline(args, vols_dev, gcm_host, aux_host, zf, zh, budget_s=12.0, ncols=64):
+def cpu_baseline(args, vols_dev, gcm_host, aux_host, zf, zh, budget_s=12.0, ncols=None):
     """Single-core CPU legs on a bounded sample of THIS run's inputs (the first `ncols` columns, copied back from the
     device): the unmodified reference (kind "reference") and the numpy port."""
-    ncols = min(ncols, vols_dev[0].shape[0])
+    ncols = min(ncols or min(64, REF_COLS[args.config]), vols_dev[0].shape[0])
     from sp_coupler_b200.constants import LES_FIELDS
     vols = {f: v[:ncols].cpu().numpy() for f, v in zip(LES_FIELDS, vols_dev)}
     if args.layout == "ijk":        # the CPU legs read the slab-contiguous view; same values
@@ -519,6 +519,10 @@ def run_b200(args):
     # ---- N>1: the round-1 weak-scaling point (the whole column count on EVERY GPU) ----
     weak = None
     if world > 1 and args.scaling == "strong" and args.weak_leg:
+        if exch is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            exch.close()
         del hp
         wjob = make_job(ncol_cfg * world)
         wp = wjob["pipe"]
@@ -527,6 +531,28 @@ def run_b200(args):
         weak = {"value": ncol_cfg * world / (ms_w * 1e-3), "unit": "columns/s", "ms_per_step": ms_w, "scaling": "weak",
                 "ncol_total": ncol_cfg * world, "ncol_per_gpu": ncol_cfg,
                 "note": "every GPU owns the whole column count of the config (round-1 bench definition)"}
+        # and its host-to-host form (shared pinned host buffer), as in the strong e2e leg
+        try:
+            whp = CouplingPipeline(cpl, zf, zh, ncol_cfg, nlev, tdt, couple_surface=True, gather=False, layout=args.layout)
+            whp.attach_les(wjob["vols"], wjob["aux"])
+            whp.les_profiles()
+            wex = HostExchange(whp, world, rank, owner=0, tag="benchweak", window=args.window, direct=args.direct)
+            ok = True
+        except Exception as e:      # noqa: BLE001
+            sys.stderr.write("rank %d: weak e2e leg unavailable (%s)\n" % (rank, e))
+            ok = False
+        if agree(ok):
+            if rank == 0:
+                wex.fill_inputs(synth.make_gcm_columns(ncol_cfg * world, nlev, seed=SEED, dtype=ndt, col0=0, ncol_total=ncol_cfg * world))
+            wex.step(DT, F_LES, F_GCM)
+            capture(whp)
+            ms_we = timed(lambda: wex.step(DT, F_LES, F_GCM), args.steps, args.warmup)
+            weak["e2e"] = {"value": ncol_cfg * world / (ms_we * 1e-3), "unit": "columns/s", "ms_per_step": ms_we,
+                           "h2d_bytes_per_step": world * whp.staging.nbytes, "d2h_bytes_per_step": world * ncol_cfg * 7 * whp.nlw * esize}
+            torch.cuda.synchronize()
+            dist.barrier()
+            wex.close()
+            del wex, whp
         del wjob, wp
         torch.cuda.empty_cache()
 
