@@ -309,6 +309,7 @@ class HostExchange(object):
         self._hdr_np, self._flags_np = self.header.numpy(), self.flags.numpy()    # plain loads for the polling loops
         self.lev0 = 0
         self.step_no = 0
+        pipe.upload_source(self.inp[rank])      # the step's H2D copy reads this rank's block of the shared buffer
         if self.registered and direct:      # K3 of this rank stores into the shared buffer and signals its flag there
             pipe.bind_host_output(self.dev_base + self._off_out, self.dev_base + self._off_flags, col0=rank * ncol, slot=rank)
         torch.distributed.barrier(group=group)
@@ -358,9 +359,10 @@ class HostExchange(object):
         self.header[1] = getattr(self, "_next_lev0", 0)
         self.header[0] = self.step_no
 
-    def fetch_inputs(self):
+    def fetch_inputs(self, stage=True):
         """All ranks, once per step (the owner after fill_inputs): wait for the step's inputs, adopt their level
-        window and stage this rank's block on its device. Returns the rank's device views (pipe.staging.dev)."""
+        window and (stage=True) copy this rank's block to its device. Returns the rank's device views
+        (pipe.staging.dev)."""
         pipe = self.pipe
         if self.rank == self.owner:
             self.publish_inputs()
@@ -372,8 +374,8 @@ class HostExchange(object):
         nlw = self.nlev - self.lev0
         if pipe.nlw != nlw:
             pipe.set_levels(nlw)
-        n = pipe.staging.numel
-        pipe.staging.dev_buf[:n].copy_(self.inp[self.rank, :n], non_blocking=True)
+        if stage:
+            pipe._upload()
         return pipe.staging.dev
 
     def wait_tendencies(self):
@@ -399,8 +401,8 @@ class HostExchange(object):
         """One sharded host-to-host step (all ranks call it; the owner refreshes the inputs with fill_inputs()
         beforehand when the GCM has moved on). Returns (forcings, out, lev0): `out` [world*ncol][7][nlev-lev0] is
         complete on the owner only; tendencies of the levels above lev0 are zero."""
-        self.fetch_inputs()
-        frc = self.pipe.step(dt, f_les, f_gcm)
+        self.fetch_inputs(stage=False)
+        frc = self.pipe.step(dt, f_les, f_gcm, upload=True)      # H2D of this rank's block + K2 -> K1 -> K3: one graph launch
         return frc, self.wait_tendencies(), self.lev0
 
 
@@ -467,7 +469,8 @@ class CouplingPipeline(object):
         elif self.gather:
             self._all_buf = torch.zeros(ncol * self.world * 7 * nlev, dtype=dtype, device=dev)
         self.k1_events = None       # optional [(start, end)] CUDA events around K1 (bench roofline)
-        self._graphs = {}           # (nlw, dt, f_les, f_gcm) -> (graph, forcings, launches)
+        self._graphs = {}           # (nlw, dt, f_les, f_gcm, with upload) -> (graph, forcings, launches)
+        self._upload_src = None     # host side of the step's H2D copy when it is not the own staging buffer
         self._out_cache = {}        # nlw -> (K2 outputs, K3 outputs): written in place every step
         self.set_levels(nlev)
 
@@ -569,10 +572,17 @@ class CouplingPipeline(object):
         self.tendencies(frc, dt, f_gcm)
         return frc
 
-    def step(self, dt=900.0, f_les=1.0, f_gcm=1.0):
+    def step(self, dt=900.0, f_les=1.0, f_gcm=1.0, upload=False):
         """The device step: replayed from its CUDA graph when one has been captured for the current level window
-        and factors, else launched eagerly."""
-        g = self._graphs.get((self.nlw, dt, f_les, f_gcm))
+        and factors, else launched eagerly. upload=True: the H2D copy of the staged GCM columns is part of the step
+        (recorded into the graph by capture(upload=True), else issued here)."""
+        g = None
+        if upload:
+            g = self._graphs.get((self.nlw, dt, f_les, f_gcm, True))
+            if g is None:
+                self._upload()
+        if g is None:
+            g = self._graphs.get((self.nlw, dt, f_les, f_gcm, False))
         if g is None:
             return self.step_device(dt, f_les, f_gcm)
         graph, frc, launches = g
@@ -582,12 +592,28 @@ class CouplingPipeline(object):
             self.epoch += 1
         return frc
 
+    def _upload(self):
+        """H2D of the staged level window from the step's host source (the pinned staging buffer, or the block of a
+        shared exchange buffer set with upload_source)."""
+        n = self.staging.numel
+        src = self._upload_src if self._upload_src is not None else self.staging.host_buf
+        self.staging.dev_buf[:n].copy_(src[:n], non_blocking=True)
+
+    def upload_source(self, src):
+        """Use `src` (a pinned / registered CPU tensor laid out like the staging buffer) as the host side of the step's
+        H2D copy instead of the pipeline's own pinned staging buffer."""
+        self._upload_src = src
+        for k in [k for k in self._graphs if k[4]]:
+            del self._graphs[k]
+
     # CUDA graph of the device step ---------------------------------------------------------------
-    def capture(self, dt=900.0, f_les=1.0, f_gcm=1.0, warmup=2):
+    def capture(self, dt=900.0, f_les=1.0, f_gcm=1.0, warmup=2, upload=False):
         """Records K2 -> K1 -> K3 once into a CUDA graph, so that a step is one graph launch instead of three calls
         through the C ABI. Sharded steps are captured too: the gather and its barrier are inside K3. All ranks must
         call it together (the warm-up steps run the device barrier). All buffers of the step are static: `step()`
-        returns the same forcing tensors every time. Only the NCCL gather mode keeps the eager path."""
+        returns the same forcing tensors every time. Only the NCCL gather mode keeps the eager path.
+        upload=True records the H2D copy of the staged level window (from the upload source) as the graph's first
+        node: the host-facing step is then ONE launch."""
         if self.gather and self.gather_mode == "nccl":
             raise RuntimeError("capture() needs the fused gather (gather='p2p' / 'p2p-owner'): the NCCL collective is "
                                "not recorded into the step graph")
@@ -598,19 +624,23 @@ class CouplingPipeline(object):
         side.wait_stream(cur)
         with torch.cuda.stream(side):          # warm-up off the capture: output buffers exist, allocator pools are warm
             for _ in range(max(warmup, 1)):
+                if upload:
+                    self._upload()
                 self.step_device(dt, f_les, f_gcm)
         cur.wait_stream(side)
         l0 = self.cpl.launches
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
+            if upload:
+                self._upload()
             frc = self.step_device(dt, f_les, f_gcm)
-        self._graphs[(self.nlw, dt, f_les, f_gcm)] = (graph, frc, self.cpl.launches - l0)
+        self._graphs[(self.nlw, dt, f_les, f_gcm, bool(upload))] = (graph, frc, self.cpl.launches - l0)
         self.cpl.launches = l0
         return graph
 
     def step_graph(self, dt=900.0, f_les=1.0, f_gcm=1.0):
         """Replays the captured step on the current stream; returns the (static) forcing tensors."""
-        if (self.nlw, dt, f_les, f_gcm) not in self._graphs:
+        if (self.nlw, dt, f_les, f_gcm, False) not in self._graphs:
             raise RuntimeError("no graph captured for this level window / factors")
         return self.step(dt, f_les, f_gcm)
 
@@ -645,8 +675,7 @@ class CouplingPipeline(object):
         with tend_host [ncol*world][7][nlw] for the current window (levels above it are zero).
         After bind_host_output() K3 writes tend_host itself and the host only polls the completion flag; otherwise the
         (gathered) device block is copied back and the stream synchronised."""
-        self.staging.upload()
-        frc = self.step(dt, f_les, f_gcm)
+        frc = self.step(dt, f_les, f_gcm, upload=True)
         if self._host_flags is not None:
             fl, want = self._host_flags_np, self.epoch
             _spin_until(lambda: int(fl[_abi.SYNC_FLAG0]), want, 60.0, "step_host: K3 completion flag")

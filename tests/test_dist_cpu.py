@@ -106,14 +106,24 @@ class _OraclePipe(object):
     def __init__(self, staging, col0):
         self.staging, self.ncol, self.col0 = staging, staging.ncol, col0
         self.epoch = 0
+        self._upload_src = None
         self.set_levels(NLEV)
+
+    def upload_source(self, src):
+        self._upload_src = src
+
+    def _upload(self):
+        n = self.staging.numel
+        self.staging.dev_buf[:n].copy_(self._upload_src[:n])
 
     def set_levels(self, nlw):
         self.staging.set_levels(nlw)
         self.nlw = nlw
         self.tend = torch.zeros((self.ncol, 7, nlw), dtype=torch.float64)
 
-    def step(self, dt, f_les, f_gcm):
+    def step(self, dt, f_les, f_gcm, upload=False):
+        if upload:
+            self._upload()
         zf, zh = synth.les_grid(NK, 200.0)
         gcm = {k: v.numpy() for k, v in self.staging.dev.items()}
         aux = synth.make_les_aux(self.ncol, NK, seed=5, col0=self.col0, ncol_total=NCOL)

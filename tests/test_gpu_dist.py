@@ -110,7 +110,7 @@ def _worker(rank, world, port, outdir):
                 if rank == 0:
                     ex.fill_inputs(gcm_all)
                 ex.step(900.0, 1.0, 1.0)
-                hp.capture(900.0, 1.0, 1.0)
+                hp.capture(900.0, 1.0, 1.0, upload=True)      # H2D of the rank's block is the graph's first node
             for it in range(STEPS):
                 hv[1].mul_(1.0 + 1e-3 * (it + 1))
                 hv[2].mul_(1.0 + 1e-2 * (it + 1))

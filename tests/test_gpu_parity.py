@@ -443,9 +443,8 @@ def test_level_window_host_step(cpl, cuda_device, nlev, graph):
     lev0 = win.stage_host(gcm)                     # picks the window, packs the cut columns into pinned staging
     win.bind_host_output()                         # K3 -> pinned host memory + flag
     assert win.nlw == nlev - lev0 and win.staging.nbytes < full_pipe.staging.nbytes or lev0 == 0
-    if graph:
-        win.staging.upload()
-        win.capture(900.0, 1.0, 1.0)
+    if graph:       # the host-facing step as ONE launch: H2D of the window + K2 -> K1 -> K3 in one graph
+        win.capture(900.0, 1.0, 1.0, upload=True)
     for it in range(3):
         f_full, t_full = full_pipe.step_host(900.0, 1.0, 1.0)
         t_full = t_full.clone()
