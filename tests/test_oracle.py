@@ -206,3 +206,39 @@ def test_slab_mean_matches_the_reference_held_expression():
                 assert np.array_equal(cnt[0], z["cnt_%g" % thr])
             for f in vols:
                 assert relerr(prof[f][0], z["mean_" + f]) <= 1e-15, (f, layout, dt)
+
+
+@pytest.mark.parametrize("nlev,nk,dz", [(19, 20, 200.0), (91, 160, 25.0), (137, 160, 25.0)])
+def test_level_window_is_exact_in_the_oracle(nlev, nk, dz):
+    """The level window of sp_coupler_b200/pipeline.py, checked on the CPU restatement of the reference alone: cutting
+    the GCM columns off above the first level over the LES top (lev0 = min start_index - 1, the host-side bound
+    `first_live_level`) changes no forcing, no cloud count and no tendency of the remaining levels - bit for bit - and
+    everything above lev0 is zero in the full result (spcpl.py:494-533). This is what lets only 26 of 91 (38 of 137)
+    levels cross PCIe / NVLink."""
+    import synth_les
+    from sp_coupler_b200 import synth
+    from sp_coupler_b200.pipeline import GcmStaging, first_live_level, window_columns
+    ncol, nx = 5, 8
+    zf, zh = synth.les_grid(nk, dz)
+    gcm = synth.make_gcm_columns(ncol, nlev, seed=31, dtype=np.float32)
+    aux = synth.make_les_aux(ncol, nk, seed=31, dtype=np.float32)
+    vols = synth_les.make_les_volumes(gcm, zf, nx, nx, seed=31, dtype=np.float32)
+    full = nb.coupling_step(gcm, zf, zh, vols, aux, aux["PS"], 900.0, 1.0, 1.0, True)
+    lev0 = first_live_level(gcm["Zgfull"], gcm["Zghalf"][:, -1], float(zf[-1]))
+    assert lev0 == max(int(full["tendencies"]["start_index"].min()) - 1, 0) and lev0 > 0
+    win = nb.coupling_step(window_columns(gcm, lev0), zf, zh, vols, aux, aux["PS"], 900.0, 1.0, 1.0, True)
+    for k in FORCING_KEYS:
+        assert np.array_equal(win["forcings"][k], full["forcings"][k]), k
+    for k in TEND_KEYS:
+        assert np.array_equal(win["tendencies"][k], full["tendencies"][k][:, lev0:]), k
+        assert not full["tendencies"][k][:, :lev0].any(), k
+    assert np.array_equal(win["tendencies"]["start_index"], full["tendencies"]["start_index"] - lev0)
+    assert np.array_equal(win["cntslab"], full["cntslab"][:, :nlev - lev0])         # ascending slabs: the lowest ones
+    assert np.array_equal(win["slab_idx"], full["slab_idx"][:, :nlev - lev0])
+    assert np.array_equal(win["cnt"], full["cnt"])
+    # the packed staging layout of a window is a contiguous prefix of the full-size buffers
+    st = GcmStaging(ncol, nlev, __import__("torch").float32, "cpu", pin=False)
+    st.set_levels(nlev - lev0)
+    st.fill_host(window_columns(gcm, lev0))
+    assert st.numel == GcmStaging.numel_for(ncol, nlev - lev0) < st.host_buf.numel()
+    assert np.array_equal(st.host["T"].numpy(), gcm["T"][:, lev0:]) and st.host["Zghalf"].shape == (ncol, nlev - lev0 + 1)
