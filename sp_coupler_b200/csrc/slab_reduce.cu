@@ -293,17 +293,19 @@ __global__ void __launch_bounds__(R::kWarps * 32, 1) slab_reduce_tma_kernel(cons
 // many warps are needed to keep the same bytes in flight. This variant streams PAIRS of consecutive slabs as one
 // 8 KB copy per warp (12 warps), reduces the two halves into separate accumulators, hands the stage back and only
 // then runs the two slab epilogues (shuffle butterflies, divide, stores), so they overlap with the next fetch.
-template <typename T, int WARPS>
+template <typename T, int WARPS, int STAGES = 1>
 __global__ void __launch_bounds__(WARPS * 32, 1) slab_reduce_tma_pair_kernel(const K1Args a) {
   constexpr int kChunk = 2 * kSubBytes;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * kChunk);
+  // [WARPS][STAGES][kChunk] data, then [WARPS][STAGES] mbarriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * STAGES * kChunk);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* wbuf = smem + (size_t)warp * kChunk;
+  uint8_t* wbuf = smem + (size_t)warp * STAGES * kChunk;
   const uint32_t wbuf_s = smem_u32(wbuf);
-  const uint32_t bar = smem_u32(bars + warp);
+  const uint32_t bar0 = smem_u32(bars + warp * STAGES);
   if (lane == 0) {
-    mbar_init(bar, 1);
+#pragma unroll
+    for (int sg = 0; sg < STAGES; ++sg) mbar_init(bar0 + 8 * sg, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -318,39 +320,49 @@ __global__ void __launch_bounds__(WARPS * 32, 1) slab_reduce_tma_pair_kernel(con
   long long rem = p0 - (long long)f * half_field;
   int pf = f;                                   // producer cursor (lane 0 advances it when it issues a copy)
   long long prem = rem;
-  auto issue = [&]() {
+  auto issue = [&](int sg) {
     const uint8_t* src = static_cast<const uint8_t*>(field_ptr(a, pf)) + (size_t)prem * kChunk;
+    const uint32_t bar = bar0 + 8 * sg;
     mbar_arrive_expect_tx(bar, (uint32_t)kChunk);
-    tma_bulk_g2s(wbuf_s, src, (uint32_t)kChunk, bar, pol);
+    tma_bulk_g2s(wbuf_s + sg * kChunk, src, (uint32_t)kChunk, bar, pol);
     prem += nwarps;
     while (prem >= half_field) {
       prem -= half_field;
       ++pf;
     }
   };
-  if (lane == 0) issue();
+  if (lane == 0) {
+#pragma unroll
+    for (int sg = 0; sg < STAGES; ++sg)
+      if (sg < npair) issue(sg);
+  }
   uint32_t parity = 0;
+  int stage = 0;
   for (long long i = 0; i < npair; ++i) {
     const long long s0 = 2 * rem;               // first slab of the pair within the field (= c*nk + k)
     const bool is_ql = (f == SPC_QL) && (a.cnt != nullptr || a.mask != nullptr);
     double accA[4] = {0.0, 0.0, 0.0, 0.0}, accB[4] = {0.0, 0.0, 0.0, 0.0};
     int cntA = 0, cntB = 0;
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait(bar0 + 8 * stage, parity)) {
     }
-    parity ^= 1;
+    const uint8_t* sbuf = wbuf + stage * kChunk;
     if (is_ql) {
-      const uint32_t bitsA = consume<T, true>(wbuf, kSubBytes >> 4, lane, accA, cntA, a.thr);
-      const uint32_t bitsB = consume<T, true>(wbuf + kSubBytes, kSubBytes >> 4, lane, accB, cntB, a.thr);
+      const uint32_t bitsA = consume<T, true>(sbuf, kSubBytes >> 4, lane, accA, cntA, a.thr);
+      const uint32_t bitsB = consume<T, true>(sbuf + kSubBytes, kSubBytes >> 4, lane, accB, cntB, a.thr);
       if (a.mask) {
         a.mask[(size_t)s0 * 32 + lane] = bitsA;
         a.mask[(size_t)(s0 + 1) * 32 + lane] = bitsB;
       }
     } else {
-      consume<T, false>(wbuf, kSubBytes >> 4, lane, accA, cntA, a.thr);
-      consume<T, false>(wbuf + kSubBytes, kSubBytes >> 4, lane, accB, cntB, a.thr);
+      consume<T, false>(sbuf, kSubBytes >> 4, lane, accA, cntA, a.thr);
+      consume<T, false>(sbuf + kSubBytes, kSubBytes >> 4, lane, accB, cntB, a.thr);
     }
     __syncwarp();  // every lane is done reading the stage before it is refilled
-    if (lane == 0 && i + 1 < npair) issue();
+    if (lane == 0 && i + STAGES < npair) issue(stage);
+    if (++stage == STAGES) {
+      stage = 0;
+      parity ^= 1;
+    }
     const double sA = warp_sum((accA[0] + accA[1]) + (accA[2] + accA[3]));
     const double sB = warp_sum((accB[0] + accB[1]) + (accB[2] + accB[3]));
     if (is_ql && a.cnt) {
@@ -937,20 +949,21 @@ int launch_tma(spc_handle h, const K1Args& a, cudaStream_t st) {
   return SPC_OK;
 }
 
-template <int W>
+template <int W, int ST>
 constexpr size_t pair_smem() {
-  return (size_t)W * 2 * kSubBytes + (size_t)W * 8;
+  return (size_t)W * ST * 2 * kSubBytes + (size_t)W * ST * 8;
 }
-template <typename T, int W>
+template <typename T, int W, int ST = 1>
 int configure_tma_pair() {
-  SPC_CUDA(cudaFuncSetAttribute(slab_reduce_tma_pair_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem<W>()));
+  SPC_CUDA(cudaFuncSetAttribute(slab_reduce_tma_pair_kernel<T, W, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)pair_smem<W, ST>()));
   return SPC_OK;
 }
-template <typename T, int W>
+template <typename T, int W, int ST = 1>
 int launch_tma_pair(spc_handle h, const K1Args& a, cudaStream_t st) {
   const long long want = ((a.total >> 1) + W - 1) / W;
   const int grid = (int)std::min<long long>(h->num_sms, std::max<long long>(want, 1));
-  slab_reduce_tma_pair_kernel<T, W><<<grid, W * 32, pair_smem<W>(), st>>>(a);
+  slab_reduce_tma_pair_kernel<T, W, ST><<<grid, W * 32, pair_smem<W, ST>(), st>>>(a);
   return SPC_OK;
 }
 
@@ -993,7 +1006,7 @@ int launch_kji(spc_handle h, const K1Args& a, bool fast, cudaStream_t st) {
     slab_reduce_generic_kernel<T><<<grid, 256, 0, st>>>(a);
   } else
 #ifdef SPC_TUNING
-  if (h->k1_variant != 0 && !(a.slab_bytes == kSubBytes && a.per_field % 2 == 0 && (h->k1_variant == 9 || h->k1_variant == 22))) {
+  if (h->k1_variant != 0 && !(a.slab_bytes == kSubBytes && a.per_field % 2 == 0 && (h->k1_variant == 9 || (h->k1_variant >= 22 && h->k1_variant <= 25)))) {
     switch (h->k1_variant) {
 #define X(id, w, c, s, b) case id: rc = launch_tma<T, Ring<w, c, s, b>>(h, a, st); break;
       SPC_K1_VARIANTS(X)
@@ -1005,6 +1018,12 @@ int launch_kji(spc_handle h, const K1Args& a, bool fast, cudaStream_t st) {
     }
   } else if (h->k1_variant == 22) {
     rc = launch_tma_pair<T, 16>(h, a, st);
+  } else if (h->k1_variant == 23) {
+    rc = launch_tma_pair<T, 8, 2>(h, a, st);
+  } else if (h->k1_variant == 24) {
+    rc = launch_tma_pair<T, 12, 2>(h, a, st);
+  } else if (h->k1_variant == 25) {
+    rc = launch_tma_pair<T, 6, 3>(h, a, st);
   } else
 #endif
   if (a.slab_bytes == kSubBytes && a.per_field % 2 == 0) {
@@ -1144,6 +1163,9 @@ int configure_all() {
   SPC_K1_VARIANTS2(Y)
 #undef Y
   if ((rc = configure_tma_pair<T, 16>())) return rc;
+  if ((rc = configure_tma_pair<T, 8, 2>())) return rc;
+  if ((rc = configure_tma_pair<T, 12, 2>())) return rc;
+  if ((rc = configure_tma_pair<T, 6, 3>())) return rc;
 #define SPC_IJK_CFG(...)                                                   \
   if ((rc = configure_ijk_tma<T, 1, IjkRing<__VA_ARGS__>>())) return rc;   \
   if ((rc = configure_ijk_tma<T, 2, IjkRing<__VA_ARGS__>>())) return rc;   \
