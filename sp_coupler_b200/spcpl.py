@@ -378,6 +378,9 @@ def set_gcm_tendencies_all(gcm, batch, dt_gcm, factor=1, conservative=False, to_
     if to_host and gcm is not None and pipe.rank == 0:
         pipe.tend_host.copy_(pipe.tend_all, non_blocking=True)
         torch.cuda.current_stream(pipe.cpl.device).synchronize()
+        if pipe.sync_error():       # K3's device-side barrier gave up on a peer (20 s): the gathered block is incomplete
+            raise RuntimeError("set_gcm_tendencies_all: rank %d never signalled its tendency block (sync error %d)"
+                               % (pipe.sync_error() - 1, pipe.sync_error()))
         cols = getattr(batch, "all_grid_indices", None)
         if cols is None:
             cols = [les.grid_index for les in batch.models]
