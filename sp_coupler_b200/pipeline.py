@@ -30,7 +30,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from .constants import surf_vars
+from .constants import grav, surf_vars
 from .coupler import GCM_FULL, GCM_HALF, RemoteTargets
 
 
@@ -59,7 +59,7 @@ def first_live_level(zgfull, zg_surface, zf_top, margin=1):
     zgfull [ncol][nlev], zg_surface [ncol] (= Zghalf[:, -1]); numpy arrays or CPU tensors."""
     zgfull = torch.as_tensor(np.asarray(zgfull) if not isinstance(zgfull, torch.Tensor) else zgfull).double()
     zs = torch.as_tensor(np.asarray(zg_surface) if not isinstance(zg_surface, torch.Tensor) else zg_surface).double()
-    zf = (zgfull - zs.reshape(-1, 1)) / 9.81
+    zf = (zgfull - zs.reshape(-1, 1)) / grav
     start = (zf > float(zf_top)).sum(dim=1)
     return max(int(start.min()) - int(margin), 0)
 
@@ -322,10 +322,18 @@ class HostExchange(object):
         return bool(int(t.item()))
 
     def close(self):
+        """Unmap the shared buffer from this rank's GPU (after its queued work has finished). The pipeline must not be
+        stepped through this exchange afterwards: its K3 targets and upload source point into the buffer."""
         if self.registered:
             torch.cuda.synchronize()
             self.pipe.cpl.host_unregister(self.raw)
             self.registered = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:           # noqa: BLE001 - interpreter shutdown: the driver unmaps the memory itself
+            pass
 
     def out(self, nlw=None):
         """[world*ncol][7][nlw] view of the shared output region for the current (or given) level window."""
