@@ -157,3 +157,68 @@ def test_torch_extension_builds_and_registers_ops():
     assert ops.mask_words_per_column(0, 0, 64, 64, 160) == 64 * 64 * 4 // 4096 * 32 * 160
     for name in ("slab_reduce", "gcm_to_les", "les_to_gcm"):
         assert hasattr(ops, name)
+
+
+def test_sync_protocol_constants_match_the_header():
+    """The host mirror of the completion protocol (K3's flags: _abi.SYNC_*) must use the header's word indices."""
+    from sp_coupler_b200 import _abi
+    src = open(HEADER).read()
+    val = lambda name: int(re.search(name + r"\s*=\s*(\d+)", src).group(1))
+    assert (_abi.SYNC_EPOCH, _abi.SYNC_DONE, _abi.SYNC_ERROR, _abi.SYNC_FLAG0, _abi.SYNC_MAX_SLOTS, _abi.SYNC_WORDS) == tuple(
+        val(n) for n in ("SPC_SYNC_EPOCH", "SPC_SYNC_DONE", "SPC_SYNC_ERROR", "SPC_SYNC_FLAG0", "SPC_SYNC_MAX_SLOTS", "SPC_SYNC_WORDS"))
+    assert _abi.MAX_PEERS == int(re.search(r"#define SPC_MAX_PEERS (\d+)", src).group(1))
+    assert _abi.SYNC_FLAG0 + _abi.SYNC_MAX_SLOTS <= _abi.SYNC_WORDS
+    assert _abi.ABI_VERSION == int(re.search(r"#define SPC_ABI_VERSION (\d+)", src).group(1))
+
+
+def test_remote_targets_validation():
+    """RemoteTargets (where K3 delivers the tendency block) rejects malformed descriptions on the host, before any
+    pointer reaches the kernel."""
+    import torch
+    from sp_coupler_b200 import _abi
+    from sp_coupler_b200.coupler import RemoteTargets
+    sync = torch.zeros(_abi.SYNC_WORDS, dtype=torch.int32)
+    r = RemoteTargets([[0x1000, 0x2000], [0x3000, 0x4000]], col0=8, sync=sync, signal=[0x5000, 0x6000], slot=1, n_wait=2)
+    o = _abi.GcmTend()
+    r.fill(o)
+    assert (o.n_peers, o.n_bufs, o.peer_col0, o.n_signal, o.sync_slot, o.n_wait) == (2, 2, 8, 2, 1, 2)
+    assert o.sync == sync.data_ptr()
+    with pytest.raises(ValueError):
+        RemoteTargets([[1, 2], [3]])                                   # buffer sets of different length
+    with pytest.raises(ValueError):
+        RemoteTargets([[1], [2]])                                      # two sets alternate by epoch: need a sync block
+    with pytest.raises(ValueError):
+        RemoteTargets([list(range(1, _abi.MAX_PEERS + 2))])            # too many targets
+    with pytest.raises(ValueError):
+        RemoteTargets([[1]], sync=torch.zeros(4, dtype=torch.int32))   # short sync block
+    with pytest.raises(ValueError):
+        RemoteTargets([[1]], sync=torch.zeros(_abi.SYNC_WORDS, dtype=torch.int64))
+    empty = RemoteTargets()
+    o2 = _abi.GcmTend()
+    empty.fill(o2)
+    assert o2.n_peers == 0 and o2.n_bufs == 1 and not o2.sync
+
+
+def test_flag_polling_returns_and_times_out():
+    import threading
+    import time
+    from sp_coupler_b200.pipeline import _spin_until
+    box = [0]
+    threading.Timer(0.05, lambda: box.__setitem__(0, 3)).start()
+    t0 = time.perf_counter()
+    _spin_until(lambda: box[0], 3, 5.0, "test flag")
+    assert 0.03 < time.perf_counter() - t0 < 2.0
+    with pytest.raises(RuntimeError):
+        _spin_until(lambda: 0, 1, 0.2, "never set")
+
+
+def test_product_package_has_no_numpy_twins():
+    """Data generators that restate the reference on the CPU (numpy interp of convert_profiles, the Philox twin of the
+    set_les_state kernel) live in tests/synth_les.py; the product package neither contains nor imports them."""
+    pkg = os.path.join(ROOT, "sp_coupler_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "synth_les" not in src or f == "synth.py", f          # synth.py only mentions it in its docstring
+            assert not re.search(r"^\s*(from|import)\s+(synth_les|cases|conftest)\b", src, flags=re.M), f
+            assert "np.interp(" not in src and "numpy.interp(" not in src, f
